@@ -1,0 +1,734 @@
+// Bandwidth-bound kernels of the UNet hot path: layout ingest, weight repack, BatchNorm
+// finalise / apply (+ReLU, +MaxPool2d) and its backward, max-pool backward, bilinear
+// upsample + pad + concat (forward and gather-form backward) and Adam.
+//
+// All activation traffic is NHWC bf16 moved as 16-byte vectors (8 channels per access), one
+// read and one write per element; per-channel coefficients are fp32 and amortised over
+// several pixels per thread.  Reductions are two-stage (per-block partials, then a tiny
+// finalise kernel summing in fp64) so results are deterministic run to run.
+//
+// Reference lines each kernel replaces are cited in include/floodplanet_b200.h.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fp {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+  f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+  f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+static inline int grid_for(long work, int block, int max_blocks) {
+  long g = (work + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------
+// ingest: NCHW f32 (x n_src, concatenated along C) -> NHWC bf16, C zero-padded
+// ---------------------------------------------------------------------------
+struct IngestArgs {
+  const float* src[8];
+  unsigned char ch_src[64];  // for padded channel c: which source
+  unsigned char ch_idx[64];  // ... and which channel inside it (255 = zero pad)
+  int src_c[8];
+};
+
+__global__ void ingest_kernel(IngestArgs a, __nv_bfloat16* __restrict__ dst, int c_pad, int N,
+                              long hw) {
+  const long total = (long)N * hw;
+  for (long px = blockIdx.x * (long)blockDim.x + threadIdx.x; px < total;
+       px += (long)gridDim.x * blockDim.x) {
+    const long n = px / hw;
+    const long o = px - n * hw;
+    for (int g = 0; g < c_pad; g += 8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g + j;
+        const int ci = a.ch_idx[c];
+        float v = 0.f;
+        if (ci != 255) {
+          const int s = a.ch_src[c];
+          v = __ldg(a.src[s] + ((long)n * a.src_c[s] + ci) * hw + o);
+        }
+        f[j] = v;
+      }
+      *reinterpret_cast<uint4*>(dst + px * c_pad + g) = pack8(f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// weight repack
+// ---------------------------------------------------------------------------
+__global__ void repack_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                    int Cout, int Cin, int cin_pad) {
+  const long total = (long)Cout * 9 * cin_pad;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int ci = i % cin_pad;
+    const int tap = (i / cin_pad) % 9;
+    const int co = i / (9L * cin_pad);
+    const float v = ci < Cin ? w[((long)co * Cin + ci) * 9 + tap] : 0.f;
+    out[i] = __float2bfloat16(v);
+  }
+}
+// out[ci][tap'][co] = w[co][ci][2-r'][2-s']  (tap' = 3 r' + s'  ->  source tap = 8 - tap')
+__global__ void repack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                    int Cout, int Cin) {
+  const long total = (long)Cin * 9 * Cout;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int co = i % Cout;
+    const int tap = (i / Cout) % 9;
+    const int ci = i / (9L * Cout);
+    out[i] = __float2bfloat16(w[((long)co * Cin + ci) * 9 + (8 - tap)]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BatchNorm statistics finalise (one warp per channel, fp64 accumulation)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int P, int C,
+                                         double count, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta,
+                                         const float* __restrict__ conv_bias, float eps,
+                                         float momentum, float* running_mean, float* running_var,
+                                         float* scale, float* shift, float* save_mean,
+                                         float* save_invstd) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int p = lane; p < P; p += 32) {
+    s += (double)partials[(size_t)p * 2 * C + c];
+    q += (double)partials[(size_t)p * 2 * C + C + c];
+  }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    if (save_mean) save_mean[c] = (float)mean;
+    if (save_invstd) save_invstd[c] = invstd;
+    if (running_mean) {
+      const float m_full = (float)mean + (conv_bias ? conv_bias[c] : 0.f);
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m_full;
+    }
+    if (running_var) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
+__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* conv_bias,
+                                    const float* rm, const float* rv, float eps, int C,
+                                    float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+}
+
+// ---------------------------------------------------------------------------
+// BN apply + ReLU
+// ---------------------------------------------------------------------------
+constexpr int kPixPerThread = 4;
+
+__global__ void bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, long ldy,
+                                     __nv_bfloat16* __restrict__ a, long lda,
+                                     const float* __restrict__ scale,
+                                     const float* __restrict__ shift, long num_pixels, int CG) {
+  // work item = (pixel group of kPixPerThread pixels strided by `pstride`, channel group)
+  const long pgroups = (num_pixels + kPixPerThread - 1) / kPixPerThread;
+  const long total = pgroups * CG;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int cg = i % CG;
+    const long pg = i / CG;
+    float sc[8], sh[8];
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+    uint4 in[kPixPerThread];
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+      const long px = pg + k * pgroups;
+      if (px < num_pixels) in[k] = ld_stream(y + px * ldy + cg * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+      const long px = pg + k * pgroups;
+      if (px < num_pixels) {
+        float f[8];
+        unpack8(in[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        *reinterpret_cast<uint4*>(a + px * lda + cg * 8) = pack8(f);
+      }
+    }
+  }
+}
+
+// BN apply + ReLU fused with MaxPool2d(2).  One thread = one 2x2 window x 8 channels.
+__global__ void bn_apply_relu_maxpool2_kernel(const __nv_bfloat16* __restrict__ y, long ldy,
+                                              __nv_bfloat16* __restrict__ a, long lda,
+                                              __nv_bfloat16* __restrict__ pooled, long ldp,
+                                              uint8_t* __restrict__ pool_idx,
+                                              const float* __restrict__ scale,
+                                              const float* __restrict__ shift, int N, int H, int W,
+                                              int CG) {
+  const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;  // windows incl. the ragged last row/col
+  const int Hp = H >> 1, Wp = W >> 1;
+  const long total = (long)N * Hc * Wc * CG;
+  const bool affine = scale != nullptr;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int cg = i % CG;
+    long t = i / CG;
+    const int wo = t % Wc; t /= Wc;
+    const int ho = t % Hc;
+    const int n = t / Hc;
+    float sc[8], sh[8];
+    if (affine) {
+      load8f(scale + cg * 8, sc);
+      load8f(shift + cg * 8, sh);
+    }
+    float best[8];
+    int bidx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bidx[j] = 0; }
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
+      if (h < H && w < W) {
+        const long px = ((long)n * H + h) * W + w;
+        float f[8];
+        unpack8(ld_stream(y + px * ldy + cg * 8), f);
+        if (affine) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+          // round through bf16 so the pooled value equals the stored activation bit for bit
+          const uint4 packed = pack8(f);
+          if (a != nullptr) *reinterpret_cast<uint4*>(a + px * lda + cg * 8) = packed;
+          unpack8(packed, f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (f[j] > best[j] || f[j] != f[j]) { best[j] = f[j]; bidx[j] = pos; }
+        }
+      }
+    }
+    if (ho < Hp && wo < Wp) {
+      const long pp = ((long)n * Hp + ho) * Wp + wo;
+      *reinterpret_cast<uint4*>(pooled + pp * ldp + cg * 8) = pack8(best);
+      uint2 ib;
+      ib.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+      ib.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+      *reinterpret_cast<uint2*>(pool_idx + pp * (long)(CG * 8) + cg * 8) = ib;
+    }
+  }
+}
+
+__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dpooled, long lddp,
+                                    const uint8_t* __restrict__ pool_idx,
+                                    const __nv_bfloat16* __restrict__ dskip, long ldds,
+                                    __nv_bfloat16* __restrict__ dx, long lddx, int N, int H, int W,
+                                    int CG) {
+  const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
+  const int Hp = H >> 1, Wp = W >> 1;
+  const long total = (long)N * Hc * Wc * CG;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int cg = i % CG;
+    long t = i / CG;
+    const int wo = t % Wc; t /= Wc;
+    const int ho = t % Hc;
+    const int n = t / Hc;
+    const bool has_pool = ho < Hp && wo < Wp;
+    float g[8];
+    uint2 ib = make_uint2(0, 0);
+    if (has_pool) {
+      const long pp = ((long)n * Hp + ho) * Wp + wo;
+      unpack8(ld_stream(dpooled + pp * lddp + cg * 8), g);
+      ib = *reinterpret_cast<const uint2*>(pool_idx + pp * (long)(CG * 8) + cg * 8);
+    }
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
+      if (h < H && w < W) {
+        const long px = ((long)n * H + h) * W + w;
+        float f[8];
+        if (dskip != nullptr) {
+          unpack8(ld_stream(dskip + px * ldds + cg * 8), f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+        if (has_pool) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t word = j < 4 ? ib.x : ib.y;
+            const int sel = (word >> (8 * (j & 3))) & 0xFF;
+            if (sel == pos) f[j] += g[j];
+          }
+        }
+        *reinterpret_cast<uint4*>(dx + px * lddx + cg * 8) = pack8(f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BN + ReLU backward
+// ---------------------------------------------------------------------------
+constexpr int kBnBwdThreads = 256;
+
+__global__ void __launch_bounds__(kBnBwdThreads)
+bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, long ldda,
+                          const __nv_bfloat16* __restrict__ y, long ldy,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          float* __restrict__ partials, long num_pixels, int C) {
+  __shared__ float red[kBnBwdThreads * 16];
+  const int CG = C >> 3;            // channel groups (8..64), divides 256
+  const int TP = kBnBwdThreads / CG;  // pixel lanes per block
+  const int cg = threadIdx.x % CG;
+  const int pl = threadIdx.x / CG;
+  float sc[8], sh[8], mu[8], is[8];
+  load8f(scale + cg * 8, sc);
+  load8f(shift + cg * 8, sh);
+  load8f(mean + cg * 8, mu);
+  load8f(invstd + cg * 8, is);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (long px = (long)blockIdx.x * TP + pl; px < num_pixels; px += (long)gridDim.x * TP) {
+    float g[8], v[8];
+    unpack8(ld_stream(da + px * ldda + cg * 8), g);
+    unpack8(ld_stream(y + px * ldy + cg * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+      s1[j] += gg;
+      s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[threadIdx.x * 16 + j] = s1[j];
+    red[threadIdx.x * 16 + 8 + j] = s2[j];
+  }
+  __syncthreads();
+  // thread (cg, j16) sums over the TP pixel lanes
+  for (int o = threadIdx.x; o < CG * 16; o += kBnBwdThreads) {
+    const int ocg = o >> 4, oj = o & 15;
+    float acc = 0.f;
+    for (int p = 0; p < TP; ++p) acc += red[(p * CG + ocg) * 16 + oj];
+    const int which = oj >> 3, ch = ocg * 8 + (oj & 7);
+    partials[(size_t)blockIdx.x * 2 * C + which * C + ch] = acc;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int P, int C,
+                                       double count, const float* __restrict__ scale,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* dgamma,
+                                       float* dbeta, float* coef) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int p = lane; p < P; p += 32) {
+    s += (double)partials[(size_t)p * 2 * C + c];
+    q += (double)partials[(size_t)p * 2 * C + C + c];
+  }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane == 0) {
+    if (dbeta) dbeta[c] = (float)s;
+    if (dgamma) dgamma[c] = (float)q;
+    // dy = scale*(g - c1 - xhat*c2) = scale*g - P*y - Q
+    const double c1 = s / count, c2 = q / count;
+    const double Pc = (double)scale[c] * c2 * (double)invstd[c];
+    const double Qc = (double)scale[c] * c1 - Pc * (double)mean[c];
+    coef[c] = (float)Pc;
+    coef[C + c] = (float)Qc;
+  }
+}
+
+__global__ void bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, long ldda,
+                                         const __nv_bfloat16* __restrict__ y, long ldy,
+                                         __nv_bfloat16* __restrict__ dy, long lddy,
+                                         const float* __restrict__ scale,
+                                         const float* __restrict__ shift,
+                                         const float* __restrict__ coef, long num_pixels, int CG) {
+  const int C = CG * 8;
+  const long pgroups = (num_pixels + kPixPerThread - 1) / kPixPerThread;
+  const long total = pgroups * CG;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int cg = i % CG;
+    const long pg = i / CG;
+    float sc[8], sh[8], Pc[8], Qc[8];
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+    load8f(coef + cg * 8, Pc);
+    load8f(coef + C + cg * 8, Qc);
+    uint4 gin[kPixPerThread], yin[kPixPerThread];
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+      const long px = pg + k * pgroups;
+      if (px < num_pixels) {
+        gin[k] = ld_stream(da + px * ldda + cg * 8);
+        yin[k] = ld_stream(y + px * ldy + cg * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+      const long px = pg + k * pgroups;
+      if (px < num_pixels) {
+        float g[8], v[8], o[8];
+        unpack8(gin[k], g);
+        unpack8(yin[k], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+          o[j] = fmaf(sc[j], gg, -fmaf(Pc[j], v[j], Qc[j]));
+        }
+        *reinterpret_cast<uint4*>(dy + px * lddy + cg * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bilinear x2 upsample (align_corners=True) + zero pad, written into a concat view
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_src(int dst, float ratio, int in_size, int& i0, int& i1,
+                                             float& l0, float& l1) {
+  const float src = ratio * (float)dst;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
+                                          __nv_bfloat16* __restrict__ out, long ldo, int N, int h,
+                                          int w, int Ho, int Wo, int CG, int pad_top,
+                                          int pad_left, float rh, float rw) {
+  const long total = (long)N * Ho * Wo * CG;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int cg = i % CG;
+    long t = i / CG;
+    const int wo = t % Wo; t /= Wo;
+    const int ho = t % Ho;
+    const int n = t / Ho;
+    const int uh = ho - pad_top, uw = wo - pad_left;
+    float o[8];
+    if (uh >= 0 && uh < 2 * h && uw >= 0 && uw < 2 * w) {
+      int h0, h1, w0, w1;
+      float lh0, lh1, lw0, lw1;
+      bilinear_src(uh, rh, h, h0, h1, lh0, lh1);
+      bilinear_src(uw, rw, w, w0, w1, lw0, lw1);
+      const __nv_bfloat16* base = x + (long)n * h * w * ldx + cg * 8;
+      float v00[8], v01[8], v10[8], v11[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long)h0 * w + w0) * ldx), v00);
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long)h0 * w + w1) * ldx), v01);
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long)h1 * w + w0) * ldx), v10);
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long)h1 * w + w1) * ldx), v11);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = lh0 * (lw0 * v00[j] + lw1 * v01[j]) + lh1 * (lw0 * v10[j] + lw1 * v11[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + (((long)n * Ho + ho) * Wo + wo) * ldo + cg * 8) = pack8(o);
+  }
+}
+
+// weight with which upsampled row/col `o` reads source index `i`
+__device__ __forceinline__ float bilinear_weight(int o, float ratio, int in_size, int i) {
+  int i0, i1;
+  float l0, l1;
+  bilinear_src(o, ratio, in_size, i0, i1, l0, l1);
+  return (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
+}
+
+__global__ void upsample2x_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long lddo,
+                                          __nv_bfloat16* __restrict__ dx, long lddx, int N, int h,
+                                          int w, int Ho, int Wo, int CG, int pad_top,
+                                          int pad_left, float rh, float rw) {
+  const long total = (long)N * h * w * CG;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int cg = i % CG;
+    long t = i / CG;
+    const int wi = t % w; t /= w;
+    const int hi = t % h;
+    const int n = t / h;
+    // candidate upsampled rows/cols whose 2-tap stencil can touch (hi, wi)
+    int oh_lo = 0, oh_hi = 2 * h - 1, ow_lo = 0, ow_hi = 2 * w - 1;
+    if (rh > 0.f) {
+      oh_lo = max(0, (int)floorf((float)(hi - 1) / rh) - 1);
+      oh_hi = min(2 * h - 1, (int)ceilf((float)(hi + 1) / rh) + 1);
+    }
+    if (rw > 0.f) {
+      ow_lo = max(0, (int)floorf((float)(wi - 1) / rw) - 1);
+      ow_hi = min(2 * w - 1, (int)ceilf((float)(wi + 1) / rw) + 1);
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      const float wh = bilinear_weight(oh, rh, h, hi);
+      if (wh == 0.f) continue;
+      const int ph = oh + pad_top;
+      if (ph < 0 || ph >= Ho) continue;
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        const float ww = bilinear_weight(ow, rw, w, wi);
+        if (ww == 0.f) continue;
+        const int pw = ow + pad_left;
+        if (pw < 0 || pw >= Wo) continue;
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(dout + (((long)n * Ho + ph) * Wo + pw) * lddo +
+                                                cg * 8),
+                g);
+        const float wgt = wh * ww;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, g[j], acc[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + (((long)n * h + hi) * w + wi) * lddx + cg * 8) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Adam
+// ---------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v, long n, float lr,
+                            float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+  const float step_size = lr / bc1;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+
+}  // namespace fp
+
+using namespace fp;
+
+extern "C" {
+
+int fpb200_abi_version(void) { return 1; }
+
+int fpb200_ingest_nchw_f32_to_nhwc_bf16(const float* const* srcs, const int* src_channels,
+                                        int n_src, void* dst, int c_pad, int N, int H, int W,
+                                        void* stream) {
+  if (n_src < 1 || n_src > 8 || c_pad % 8 != 0 || c_pad > 64) return FPB200_ERR_SHAPE;
+  IngestArgs a;
+  int c = 0;
+  for (int s = 0; s < 8; ++s) { a.src[s] = nullptr; a.src_c[s] = 0; }
+  for (int s = 0; s < n_src; ++s) {
+    a.src[s] = srcs[s];
+    a.src_c[s] = src_channels[s];
+    for (int k = 0; k < src_channels[s]; ++k) {
+      if (c >= c_pad) return FPB200_ERR_SHAPE;
+      a.ch_src[c] = (unsigned char)s;
+      a.ch_idx[c] = (unsigned char)k;
+      ++c;
+    }
+  }
+  for (; c < 64; ++c) { a.ch_src[c] = 0; a.ch_idx[c] = 255; }
+  const long total = (long)N * H * W;
+  ingest_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      a, (__nv_bfloat16*)dst, c_pad, N, (long)H * W);
+  return check_launch("ingest");
+}
+
+int fpb200_repack_weights_fprop(const float* w_oihw, void* w_packed, int Cout, int Cin,
+                                int cin_pad, void* stream) {
+  if (cin_pad < Cin) return FPB200_ERR_SHAPE;
+  const long total = (long)Cout * 9 * cin_pad;
+  repack_fprop_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, (__nv_bfloat16*)w_packed, Cout, Cin, cin_pad);
+  return check_launch("repack_fprop");
+}
+
+int fpb200_repack_weights_dgrad(const float* w_oihw, void* w_packed, int Cout, int Cin,
+                                void* stream) {
+  const long total = (long)Cout * 9 * Cin;
+  repack_dgrad_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, (__nv_bfloat16*)w_packed, Cout, Cin);
+  return check_launch("repack_dgrad");
+}
+
+int fpb200_bn_stats_finalize(const float* partials, int num_partials, int C, double count,
+                             const float* gamma, const float* beta, const float* conv_bias,
+                             float eps, float momentum, float* running_mean, float* running_var,
+                             float* scale, float* shift, float* save_mean, float* save_invstd,
+                             void* stream) {
+  if (C <= 0 || num_partials <= 0) return FPB200_ERR_SHAPE;
+  bn_stats_finalize_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      partials, num_partials, C, count, gamma, beta, conv_bias, eps, momentum, running_mean,
+      running_var, scale, shift, save_mean, save_invstd);
+  return check_launch("bn_stats_finalize");
+}
+
+int fpb200_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias,
+                        const float* running_mean, const float* running_var, float eps, int C,
+                        float* scale, float* shift, void* stream) {
+  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      gamma, beta, conv_bias, running_mean, running_var, eps, C, scale, shift);
+  return check_launch("bn_fold_eval");
+}
+
+int fpb200_bn_apply_relu(const void* y, long ldy, void* a, long lda, const float* scale,
+                         const float* shift, long num_pixels, int C, void* stream) {
+  if (C % 8 != 0 || ldy % 8 != 0 || lda % 8 != 0) return FPB200_ERR_SHAPE;
+  const long total = ((num_pixels + kPixPerThread - 1) / kPixPerThread) * (C / 8);
+  bn_apply_relu_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y, ldy, (__nv_bfloat16*)a, lda, scale, shift, num_pixels, C / 8);
+  return check_launch("bn_apply_relu");
+}
+
+int fpb200_bn_apply_relu_maxpool2(const void* y, long ldy, void* a, long lda, void* pooled,
+                                  long ldp, uint8_t* pool_idx, const float* scale,
+                                  const float* shift, int N, int H, int W, int C, void* stream) {
+  if (C % 8 != 0 || ldy % 8 != 0 || ldp % 8 != 0 || (a && lda % 8 != 0)) return FPB200_ERR_SHAPE;
+  const long total = (long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  bn_apply_relu_maxpool2_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y, ldy, (__nv_bfloat16*)a, lda, (__nv_bfloat16*)pooled, ldp, pool_idx,
+      scale, shift, N, H, W, C / 8);
+  return check_launch("bn_apply_relu_maxpool2");
+}
+
+int fpb200_maxpool2_bwd(const void* dpooled, long lddp, const uint8_t* pool_idx, const void* dskip,
+                        long ldds, void* dx, long lddx, int N, int H, int W, int C, void* stream) {
+  if (C % 8 != 0 || lddp % 8 != 0 || lddx % 8 != 0) return FPB200_ERR_SHAPE;
+  const long total = (long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  maxpool2_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dpooled, lddp, pool_idx, (const __nv_bfloat16*)dskip, ldds,
+      (__nv_bfloat16*)dx, lddx, N, H, W, C / 8);
+  return check_launch("maxpool2_bwd");
+}
+
+int fpb200_bn_bwd_rows(void) { return 4 * sm_count(); }
+
+int fpb200_bn_relu_bwd_reduce(const void* da, long ldda, const void* y, long ldy,
+                              const float* scale, const float* shift, const float* save_mean,
+                              const float* save_invstd, float* partials, long num_pixels, int C,
+                              void* stream) {
+  if (C % 64 != 0 || C > 2048 || (256 % (C / 8)) != 0) return FPB200_ERR_SHAPE;
+  bn_relu_bwd_reduce_kernel<<<fpb200_bn_bwd_rows(), kBnBwdThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)y, ldy, scale, shift, save_mean,
+      save_invstd, partials, num_pixels, C);
+  return check_launch("bn_relu_bwd_reduce");
+}
+
+int fpb200_bn_bwd_finalize(const float* partials, int num_partials, int C, double count,
+                           const float* scale, const float* save_mean, const float* save_invstd,
+                           float* dgamma, float* dbeta, float* coef, void* stream) {
+  bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      partials, num_partials, C, count, scale, save_mean, save_invstd, dgamma, dbeta, coef);
+  return check_launch("bn_bwd_finalize");
+}
+
+int fpb200_bn_relu_bwd_apply(const void* da, long ldda, const void* y, long ldy, void* dy,
+                             long lddy, const float* scale, const float* shift, const float* coef,
+                             long num_pixels, int C, void* stream) {
+  if (C % 8 != 0) return FPB200_ERR_SHAPE;
+  const long total = ((num_pixels + kPixPerThread - 1) / kPixPerThread) * (C / 8);
+  bn_relu_bwd_apply_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)y, ldy, (__nv_bfloat16*)dy, lddy, scale,
+      shift, coef, num_pixels, C / 8);
+  return check_launch("bn_relu_bwd_apply");
+}
+
+static inline float align_corners_ratio(int in_size, int out_size) {
+  return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+
+int fpb200_upsample2x_pad_concat_fwd(const void* x, long ldx, void* out, long ldo, int N, int h,
+                                     int w, int Ho, int Wo, int C, void* stream) {
+  if (C % 8 != 0 || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
+  const int pad_top = (Ho - 2 * h) / 2, pad_left = (Wo - 2 * w) / 2;
+  const long total = (long)N * Ho * Wo * (C / 8);
+  upsample2x_pad_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, N, h, w, Ho, Wo, C / 8, pad_top,
+      pad_left, align_corners_ratio(h, 2 * h), align_corners_ratio(w, 2 * w));
+  return check_launch("upsample2x_pad_concat_fwd");
+}
+
+int fpb200_upsample2x_pad_concat_bwd(const void* dout, long lddo, void* dx, long lddx, int N,
+                                     int h, int w, int Ho, int Wo, int C, void* stream) {
+  if (C % 8 != 0 || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
+  const int pad_top = (Ho - 2 * h) / 2, pad_left = (Wo - 2 * w) / 2;
+  const long total = (long)N * h * w * (C / 8);
+  upsample2x_pad_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx, N, h, w, Ho, Wo, C / 8, pad_top,
+      pad_left, align_corners_ratio(h, 2 * h), align_corners_ratio(w, 2 * w));
+  return check_launch("upsample2x_pad_concat_bwd");
+}
+
+int fpb200_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                     float beta2, float eps, int step, float grad_scale, void* stream) {
+  if (n <= 0 || step < 1) return FPB200_ERR_SHAPE;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  return check_launch("adam_step");
+}
+
+}  // extern "C"

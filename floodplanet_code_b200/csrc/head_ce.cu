@@ -1,0 +1,366 @@
+// OutConv 1x1 head (models/unet.py:70-77) and masked cross-entropy + argmax + confusion
+// counts (models/water_seg_model.py:40,103-109): pure bandwidth passes over the 64-channel
+// full-resolution map and the fp32 NCHW logits, with warp-shuffle reductions.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fp {
+
+constexpr int kMaxClasses = 8;
+constexpr int kHeadC = 64;
+
+__device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+  f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+  f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// ---------------------------------------------------------------------------
+// head forward: one thread per pixel, 8 x 16-byte loads, weights broadcast from smem
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const float* __restrict__ w,
+                   const float* __restrict__ b, float* __restrict__ logits, int N, long hw,
+                   int ncls) {
+  __shared__ float sw[kMaxClasses * kHeadC];
+  __shared__ float sb[kMaxClasses];
+  for (int i = threadIdx.x; i < ncls * kHeadC; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < ncls) sb[threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const long total = (long)N * hw;
+  for (long px = blockIdx.x * (long)blockDim.x + threadIdx.x; px < total;
+       px += (long)gridDim.x * blockDim.x) {
+    float acc[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
+    const uint4* row = reinterpret_cast<const uint4*>(x + px * ldx);
+#pragma unroll
+    for (int g = 0; g < kHeadC / 8; ++g) {
+      float f[8];
+      unpack8h(__ldg(row + g), f);
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k) {
+        if (k < ncls) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], sw[k * kHeadC + g * 8 + j], acc[k]);
+        }
+      }
+    }
+    const long n = px / hw, o = px - n * hw;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < ncls) logits[((long)n * ncls + k) * hw + o] = acc[k] + sb[k];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// head backward: 8 lanes x 8 channels cover one pixel, 4 pixels per warp iteration.
+//   dx[p, c]  = sum_k dl[k, p] * w[k, c]
+//   dW[k, c] += dl[k, p] * x[p, c],   db[k] += dl[k, p]
+// ---------------------------------------------------------------------------
+constexpr int kHeadBwdThreads = 256;
+
+__global__ void __launch_bounds__(kHeadBwdThreads)
+head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, long ldx,
+                   const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, long lddx,
+                   float* __restrict__ partials, int N, long hw, int ncls) {
+  __shared__ float sw[kMaxClasses * kHeadC];
+  __shared__ float red[(kHeadBwdThreads / 32) * kMaxClasses * (kHeadC + 1)];
+  for (int i = threadIdx.x; i < ncls * kHeadC; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3;  // which of the 4 pixels of this warp iteration
+  const int cg = lane & 7;    // channel group: channels cg*8 .. cg*8+7
+  float dw[kMaxClasses][8];
+  float db[kMaxClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    db[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dw[k][j] = 0.f;
+  }
+  const long total = (long)N * hw;
+  const long warps_total = (long)gridDim.x * (kHeadBwdThreads / 32);
+  for (long base = ((long)blockIdx.x * (kHeadBwdThreads / 32) + warp) * 4; base < total;
+       base += warps_total * 4) {
+    const long px = base + sub;
+    if (px < total) {
+      const long n = px / hw, o = px - n * hw;
+      float dl[kMaxClasses];
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k)
+        dl[k] = k < ncls ? __ldg(dlogits + ((long)n * ncls + k) * hw + o) : 0.f;
+      float f[8], g[8];
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(x + px * ldx + cg * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k) {
+        if (k < ncls) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            g[j] = fmaf(dl[k], sw[k * kHeadC + cg * 8 + j], g[j]);
+            dw[k][j] = fmaf(dl[k], f[j], dw[k][j]);
+          }
+          db[k] += dl[k];
+        }
+      }
+      uint4 o4;
+      o4.x = pack_bf16x2(g[0], g[1]);
+      o4.y = pack_bf16x2(g[2], g[3]);
+      o4.z = pack_bf16x2(g[4], g[5]);
+      o4.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(dx + px * lddx + cg * 8) = o4;
+    }
+  }
+  // reduce the 4 pixel sub-lanes of the warp
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dw[k][j] += __shfl_xor_sync(0xffffffffu, dw[k][j], 8);
+      dw[k][j] += __shfl_xor_sync(0xffffffffu, dw[k][j], 16);
+    }
+    db[k] += __shfl_xor_sync(0xffffffffu, db[k], 8);
+    db[k] += __shfl_xor_sync(0xffffffffu, db[k], 16);
+  }
+  const int stride = kHeadC + 1;
+  if (sub == 0) {
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(warp * kMaxClasses + k) * stride + cg * 8 + j] = dw[k][j];
+      if (cg == 0) red[(warp * kMaxClasses + k) * stride + kHeadC] = db[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncls * stride; i += blockDim.x) {
+    const int k = i / stride, c = i - k * stride;
+    float acc = 0.f;
+    for (int wv = 0; wv < kHeadBwdThreads / 32; ++wv) acc += red[(wv * kMaxClasses + k) * stride + c];
+    partials[(size_t)blockIdx.x * ncls * stride + i] = acc;
+  }
+}
+
+__global__ void head_bwd_finalize_kernel(const float* __restrict__ partials, int P, int ncls,
+                                         float* dw, float* db) {
+  const int stride = kHeadC + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncls * stride) return;
+  double acc = 0.0;
+  for (int p = 0; p < P; ++p) acc += (double)partials[(size_t)p * ncls * stride + i];
+  const int k = i / stride, c = i - k * stride;
+  if (c < kHeadC) dw[k * kHeadC + c] = (float)acc;
+  else db[k] = (float)acc;
+}
+
+// ---------------------------------------------------------------------------
+// masked softmax cross-entropy + argmax + confusion counts
+// ---------------------------------------------------------------------------
+constexpr int kCeThreads = 256;
+
+__global__ void __launch_bounds__(kCeThreads)
+softmax_ce_argmax_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
+                             long ignore_index, int64_t* __restrict__ pred,
+                             unsigned long long* __restrict__ confusion,
+                             double* __restrict__ partials, int N, int ncls, long hw) {
+  __shared__ unsigned int s_conf[kMaxClasses * kMaxClasses];
+  __shared__ double s_red[3][kCeThreads / 32];
+  if (threadIdx.x < kMaxClasses * kMaxClasses) s_conf[threadIdx.x] = 0;
+  __syncthreads();
+  double loss_sum = 0.0;
+  double cnt = 0.0, bad = 0.0;
+  const long total = (long)N * hw;
+  for (long px = blockIdx.x * (long)blockDim.x + threadIdx.x; px < total;
+       px += (long)gridDim.x * blockDim.x) {
+    const long n = px / hw, o = px - n * hw;
+    float l[kMaxClasses];
+    float best = 0.f;
+    int bi = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      if (k < ncls) {
+        l[k] = __ldg(logits + ((long)n * ncls + k) * hw + o);
+        // first maximum wins; NaN counts as the maximum (torch.argmax semantics)
+        if (k == 0 || (l[k] > best) || (l[k] != l[k] && best == best)) { best = l[k]; bi = k; }
+      }
+    }
+    const long t = target[px];
+    if (pred != nullptr) pred[px] = bi;
+    if (t != ignore_index) {
+      if (t < 0 || t >= ncls) {
+        bad += 1.0;
+      } else {
+        float mx = l[0];
+#pragma unroll
+        for (int k = 1; k < kMaxClasses; ++k)
+          if (k < ncls) mx = fmaxf(mx, l[k]);
+        float se = 0.f, lt = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+          if (k < ncls) {
+            se += expf(l[k] - mx);
+            if (k == (int)t) lt = l[k];
+          }
+        }
+        loss_sum += (double)((mx + logf(se)) - lt);
+        cnt += 1.0;
+        if (confusion != nullptr) atomicAdd(&s_conf[(int)t * kMaxClasses + bi], 1u);
+      }
+    }
+  }
+  // block reduce
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    loss_sum += __shfl_xor_sync(0xffffffffu, loss_sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if (lane == 0) { s_red[0][warp] = loss_sum; s_red[1][warp] = cnt; s_red[2][warp] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int wv = 0; wv < kCeThreads / 32; ++wv) { a += s_red[0][wv]; b += s_red[1][wv]; c += s_red[2][wv]; }
+    partials[(size_t)blockIdx.x * 4 + 0] = a;
+    partials[(size_t)blockIdx.x * 4 + 1] = b;
+    partials[(size_t)blockIdx.x * 4 + 2] = c;
+  }
+  if (confusion != nullptr && threadIdx.x < kMaxClasses * kMaxClasses) {
+    const int t = threadIdx.x / kMaxClasses, pcls = threadIdx.x % kMaxClasses;
+    const unsigned int v = s_conf[threadIdx.x];
+    if (v != 0 && t < ncls && pcls < ncls)
+      atomicAdd(&confusion[t * ncls + pcls], (unsigned long long)v);
+  }
+}
+
+__global__ void ce_finalize_kernel(const double* __restrict__ partials, int P, double* result) {
+  // single warp
+  double a = 0, b = 0, c = 0;
+  for (int p = threadIdx.x; p < P; p += 32) {
+    a += partials[(size_t)p * 4 + 0];
+    b += partials[(size_t)p * 4 + 1];
+    c += partials[(size_t)p * 4 + 2];
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (threadIdx.x == 0) {
+    result[0] = a;
+    result[1] = b;
+    result[2] = c;
+    result[3] = a / b;  // 0/0 = NaN, like torch's mean over an empty set
+  }
+}
+
+__global__ void __launch_bounds__(kCeThreads)
+softmax_ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
+                      long ignore_index, const double* __restrict__ result,
+                      const float* __restrict__ grad_out, float* __restrict__ dlogits, int N,
+                      int ncls, long hw) {
+  const double count = result[1];
+  const float go = grad_out != nullptr ? __ldg(grad_out) : 1.f;
+  const float coef = count > 0.0 ? go / (float)count : 0.f;
+  const long total = (long)N * hw;
+  for (long px = blockIdx.x * (long)blockDim.x + threadIdx.x; px < total;
+       px += (long)gridDim.x * blockDim.x) {
+    const long n = px / hw, o = px - n * hw;
+    const long t = target[px];
+    const bool active = (t != ignore_index) && t >= 0 && t < ncls && coef != 0.f;
+    float l[kMaxClasses];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      if (k < ncls) {
+        l[k] = active ? __ldg(logits + ((long)n * ncls + k) * hw + o) : 0.f;
+        mx = fmaxf(mx, l[k]);
+      }
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < ncls) { l[k] = expf(l[k] - mx); se += l[k]; }
+    const float inv = 1.f / se;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      if (k < ncls) {
+        const float g = active ? (l[k] * inv - (k == (int)t ? 1.f : 0.f)) * coef : 0.f;
+        dlogits[((long)n * ncls + k) * hw + o] = g;
+      }
+    }
+  }
+}
+
+}  // namespace fp
+
+using namespace fp;
+
+extern "C" {
+
+int fpb200_head1x1_fwd(const void* x, long ldx, const float* w, const float* b, float* logits,
+                       int N, int H, int W, int C, int n_classes, void* stream) {
+  if (C != kHeadC || n_classes < 1 || n_classes > kMaxClasses || ldx % 8 != 0)
+    return FPB200_ERR_SHAPE;
+  const long total = (long)N * H * W;
+  long g = (total + 255) / 256;
+  if (g > 148L * 16) g = 148L * 16;
+  head1x1_fwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, w, b, logits, N, (long)H * W, n_classes);
+  return check_launch("head1x1_fwd");
+}
+
+int fpb200_head_bwd_rows(void) { return 4 * sm_count(); }
+
+int fpb200_head1x1_bwd(const float* dlogits, const void* x, long ldx, const float* w, void* dx,
+                       long lddx, float* dw, float* db, float* partials, int N, int H, int W,
+                       int C, int n_classes, void* stream) {
+  if (C != kHeadC || n_classes < 1 || n_classes > kMaxClasses || ldx % 8 != 0 || lddx % 8 != 0)
+    return FPB200_ERR_SHAPE;
+  const int rows = fpb200_head_bwd_rows();
+  head1x1_bwd_kernel<<<rows, kHeadBwdThreads, 0, (cudaStream_t)stream>>>(
+      dlogits, (const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)dx, lddx, partials, N,
+      (long)H * W, n_classes);
+  int rc = check_launch("head1x1_bwd");
+  if (rc != FPB200_OK) return rc;
+  const int n = n_classes * (kHeadC + 1);
+  head_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rows,
+                                                                              n_classes, dw, db);
+  return check_launch("head1x1_bwd_finalize");
+}
+
+int fpb200_ce_rows(void) { return 8 * sm_count(); }
+
+int fpb200_softmax_ce_argmax_fwd(const float* logits, const int64_t* target, long ignore_index,
+                                 double* result, int64_t* pred, int64_t* confusion,
+                                 double* partials, int N, int n_classes, long hw, void* stream) {
+  if (n_classes < 1 || n_classes > kMaxClasses || N < 1 || hw < 1) return FPB200_ERR_SHAPE;
+  const long total = (long)N * hw;
+  long g = (total + kCeThreads - 1) / kCeThreads;
+  const int rows = fpb200_ce_rows();
+  if (g > rows) g = rows;
+  softmax_ce_argmax_fwd_kernel<<<(int)g, kCeThreads, 0, (cudaStream_t)stream>>>(
+      logits, target, ignore_index, pred, (unsigned long long*)confusion, partials, N, n_classes,
+      hw);
+  int rc = check_launch("softmax_ce_argmax_fwd");
+  if (rc != FPB200_OK) return rc;
+  ce_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, (int)g, result);
+  return check_launch("softmax_ce_finalize");
+}
+
+int fpb200_softmax_ce_bwd(const float* logits, const int64_t* target, long ignore_index,
+                          const double* result, const float* grad_out, float* dlogits, int N,
+                          int n_classes, long hw, void* stream) {
+  if (n_classes < 1 || n_classes > kMaxClasses) return FPB200_ERR_SHAPE;
+  const long total = (long)N * hw;
+  long g = (total + kCeThreads - 1) / kCeThreads;
+  if (g > 148L * 16) g = 148L * 16;
+  softmax_ce_bwd_kernel<<<(int)g, kCeThreads, 0, (cudaStream_t)stream>>>(
+      logits, target, ignore_index, result, grad_out, dlogits, N, n_classes, hw);
+  return check_launch("softmax_ce_bwd");
+}
+
+}  // extern "C"

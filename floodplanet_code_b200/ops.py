@@ -1,0 +1,299 @@
+"""Tensor-level wrappers over the C ABI (``capi``): they only translate torch tensors into
+(pointer, pitch, dims, stream) and raise on a non-zero status.  All arithmetic happens in
+the CUDA kernels of ``csrc/``; nothing here computes on the CPU or through torch ops.
+
+NHWC bf16 activation *views* are torch tensors of shape [N, H, W, C] whose last dimension is
+contiguous and whose pixel pitch ``stride(2)`` may exceed C (a channel slice of a concat
+buffer).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import capi
+
+
+def _lib():
+    return capi.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "floodplanet_b200: tensors must live on a CUDA device (sm_100a); there is no "
+                "CPU fallback for this path")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def nhwc_view(t: torch.Tensor) -> Tuple[int, int]:
+    """(device pointer, pixel pitch) of an NHWC bf16 view; validates the layout."""
+    if t.dtype != torch.bfloat16 or t.dim() != 4:
+        raise RuntimeError(f"expected a bf16 [N,H,W,C] view, got {t.dtype} {tuple(t.shape)}")
+    n, h, w, c = t.shape
+    ld = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if n > 1 else c))
+    ok = t.stride(3) == 1 and (w == 1 or t.stride(2) == ld) and (h == 1 or t.stride(1) == ld * w) \
+        and (n == 1 or t.stride(0) == ld * w * h)
+    if not ok or ld % 8 != 0 or t.data_ptr() % 16 != 0:
+        raise RuntimeError(f"not a dense-pitch NHWC view: shape {tuple(t.shape)} strides {t.stride()}")
+    return t.data_ptr(), ld
+
+
+def stat_rows() -> int:
+    return _lib().fpb200_conv_stat_rows()
+
+
+def bn_bwd_rows() -> int:
+    return _lib().fpb200_bn_bwd_rows()
+
+
+def head_bwd_rows() -> int:
+    return _lib().fpb200_head_bwd_rows()
+
+
+def ce_rows() -> int:
+    return _lib().fpb200_ce_rows()
+
+
+# ------------------------------------------------------------------------------------------
+def ingest(srcs: Sequence[torch.Tensor], c_pad: int) -> torch.Tensor:
+    """NCHW fp32 image(s) -> NHWC bf16 [N,H,W,c_pad] (early-fusion concat + cast + pad)."""
+    _require_cuda(*srcs)
+    n, _, h, w = srcs[0].shape
+    srcs = [s.contiguous() if s.dtype == torch.float32 else s.float().contiguous() for s in srcs]
+    for s in srcs:
+        if s.dim() != 4 or s.shape[0] != n or s.shape[2] != h or s.shape[3] != w:
+            raise RuntimeError(f"ingest: inconsistent source shapes {[tuple(x.shape) for x in srcs]}")
+    out = torch.empty((n, h, w, c_pad), dtype=torch.bfloat16, device=srcs[0].device)
+    k = len(srcs)
+    ptrs = (C.c_void_p * k)(*[s.data_ptr() for s in srcs])
+    chans = (C.c_int * k)(*[s.shape[1] for s in srcs])
+    st = _lib().fpb200_ingest_nchw_f32_to_nhwc_bf16(ptrs, chans, k, out.data_ptr(), c_pad, n, h, w,
+                                                    _stream())
+    capi.check(st, "ingest_nchw_f32_to_nhwc_bf16", N=n, H=h, W=w, c_pad=c_pad,
+               channels=[s.shape[1] for s in srcs])
+    return out
+
+
+def repack_fprop(w: torch.Tensor, cin_pad: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(w)
+    cout, cin = w.shape[0], w.shape[1]
+    if out is None:
+        out = torch.empty((cout, 9, cin_pad), dtype=torch.bfloat16, device=w.device)
+    st = _lib().fpb200_repack_weights_fprop(w.detach().contiguous().data_ptr(), out.data_ptr(), cout,
+                                            cin, cin_pad, _stream())
+    capi.check(st, "repack_weights_fprop", Cout=cout, Cin=cin, cin_pad=cin_pad)
+    return out
+
+
+def repack_dgrad(w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(w)
+    cout, cin = w.shape[0], w.shape[1]
+    if out is None:
+        out = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device=w.device)
+    st = _lib().fpb200_repack_weights_dgrad(w.detach().contiguous().data_ptr(), out.data_ptr(), cout,
+                                            cin, _stream())
+    capi.check(st, "repack_weights_dgrad", Cout=cout, Cin=cin)
+    return out
+
+
+def conv3x3_fprop(x: torch.Tensor, w_packed: torch.Tensor, y: torch.Tensor,
+                  scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+                  relu: bool = False, stat_partials: Optional[torch.Tensor] = None) -> None:
+    _require_cuda(x, w_packed, y)
+    xp, ldx = nhwc_view(x)
+    yp, ldy = nhwc_view(y)
+    n, h, w, cin = x.shape
+    cout = y.shape[3]
+    if w_packed.shape != (cout, 9, cin):
+        raise RuntimeError(f"conv3x3_fprop: packed weight {tuple(w_packed.shape)} != ({cout}, 9, {cin})")
+    st = _lib().fpb200_conv3x3_fprop_bf16_nhwc(xp, ldx, w_packed.data_ptr(), yp, ldy, n, h, w, cin,
+                                               cout, _ptr(scale), _ptr(shift), int(relu),
+                                               _ptr(stat_partials), _stream())
+    capi.check(st, "conv3x3_fprop_bf16_nhwc", N=n, H=h, W=w, Cin=cin, Cout=cout)
+
+
+def conv3x3_dgrad(dy: torch.Tensor, w_packed_dgrad: torch.Tensor, dx: torch.Tensor) -> None:
+    _require_cuda(dy, w_packed_dgrad, dx)
+    dyp, lddy = nhwc_view(dy)
+    dxp, lddx = nhwc_view(dx)
+    n, h, w, cout = dy.shape
+    cin = dx.shape[3]
+    st = _lib().fpb200_conv3x3_dgrad_bf16_nhwc(dyp, lddy, w_packed_dgrad.data_ptr(), dxp, lddx, n, h,
+                                               w, cout, cin, _stream())
+    capi.check(st, "conv3x3_dgrad_bf16_nhwc", N=n, H=h, W=w, Cout=cout, Cin=cin)
+
+
+def wgrad_workspace_bytes(n: int, h: int, w: int, cin: int, cout: int) -> int:
+    b = _lib().fpb200_conv3x3_wgrad_workspace_bytes(n, h, w, cin, cout)
+    if b < 0:
+        raise RuntimeError(f"conv3x3_wgrad: unsupported shape Cin={cin} Cout={cout}")
+    return b
+
+
+def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, workspace: torch.Tensor,
+                  cin_real: int) -> None:
+    """dw (fp32 [Cout, cin_real, 3, 3], contiguous) is overwritten."""
+    _require_cuda(x, dy, dw, workspace)
+    xp, ldx = nhwc_view(x)
+    dyp, lddy = nhwc_view(dy)
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    need = wgrad_workspace_bytes(n, h, w, cin, cout)
+    if workspace.numel() * workspace.element_size() < need or not dw.is_contiguous():
+        raise RuntimeError("conv3x3_wgrad: workspace too small or dw not contiguous")
+    st = _lib().fpb200_conv3x3_wgrad_bf16_nhwc(xp, ldx, dyp, lddy, dw.data_ptr(), workspace.data_ptr(),
+                                               n, h, w, cin, cin_real, cout, _stream())
+    capi.check(st, "conv3x3_wgrad_bf16_nhwc", N=n, H=h, W=w, Cin=cin, Cout=cout)
+
+
+# ------------------------------------------------------------------------------------------
+def bn_stats_finalize(partials, count, gamma, beta, conv_bias, eps, momentum, running_mean,
+                      running_var, scale, shift, save_mean, save_invstd) -> None:
+    c = gamma.numel()
+    st = _lib().fpb200_bn_stats_finalize(partials.data_ptr(), partials.shape[0], c, float(count),
+                                         gamma.data_ptr(), beta.data_ptr(), _ptr(conv_bias), eps,
+                                         momentum, _ptr(running_mean), _ptr(running_var),
+                                         scale.data_ptr(), shift.data_ptr(), _ptr(save_mean),
+                                         _ptr(save_invstd), _stream())
+    capi.check(st, "bn_stats_finalize", C=c, count=count)
+
+
+def bn_fold_eval(gamma, beta, conv_bias, running_mean, running_var, eps, scale, shift) -> None:
+    c = gamma.numel()
+    st = _lib().fpb200_bn_fold_eval(gamma.data_ptr(), beta.data_ptr(), _ptr(conv_bias),
+                                    running_mean.data_ptr(), running_var.data_ptr(), eps, c,
+                                    scale.data_ptr(), shift.data_ptr(), _stream())
+    capi.check(st, "bn_fold_eval", C=c)
+
+
+def bn_apply_relu(y, a, scale, shift) -> None:
+    yp, ldy = nhwc_view(y)
+    ap, lda = nhwc_view(a)
+    n, h, w, c = y.shape
+    st = _lib().fpb200_bn_apply_relu(yp, ldy, ap, lda, scale.data_ptr(), shift.data_ptr(), n * h * w, c,
+                                     _stream())
+    capi.check(st, "bn_apply_relu", N=n, H=h, W=w, C=c)
+
+
+def bn_apply_relu_maxpool2(y, a, pooled, pool_idx, scale, shift) -> None:
+    """y -> a = relu(y*scale+shift) (a may be None), pooled = maxpool2(a), pool_idx (uint8)."""
+    yp, ldy = nhwc_view(y)
+    ap, lda = nhwc_view(a) if a is not None else (None, 0)
+    pp, ldp = nhwc_view(pooled)
+    n, h, w, c = y.shape
+    st = _lib().fpb200_bn_apply_relu_maxpool2(yp, ldy, ap, lda, pp, ldp, pool_idx.data_ptr(),
+                                              _ptr(scale), _ptr(shift), n, h, w, c, _stream())
+    capi.check(st, "bn_apply_relu_maxpool2", N=n, H=h, W=w, C=c)
+
+
+def maxpool2_bwd(dpooled, pool_idx, dskip, dx) -> None:
+    dpp, lddp = nhwc_view(dpooled)
+    dsp, ldds = nhwc_view(dskip) if dskip is not None else (None, 0)
+    dxp, lddx = nhwc_view(dx)
+    n, h, w, c = dx.shape
+    st = _lib().fpb200_maxpool2_bwd(dpp, lddp, pool_idx.data_ptr(), dsp, ldds, dxp, lddx, n, h, w, c,
+                                    _stream())
+    capi.check(st, "maxpool2_bwd", N=n, H=h, W=w, C=c)
+
+
+def bn_relu_bwd_reduce(da, y, scale, shift, save_mean, save_invstd, partials) -> None:
+    dap, ldda = nhwc_view(da)
+    yp, ldy = nhwc_view(y)
+    n, h, w, c = y.shape
+    st = _lib().fpb200_bn_relu_bwd_reduce(dap, ldda, yp, ldy, scale.data_ptr(), shift.data_ptr(),
+                                          save_mean.data_ptr(), save_invstd.data_ptr(),
+                                          partials.data_ptr(), n * h * w, c, _stream())
+    capi.check(st, "bn_relu_bwd_reduce", N=n, H=h, W=w, C=c)
+
+
+def bn_bwd_finalize(partials, count, scale, save_mean, save_invstd, dgamma, dbeta, coef) -> None:
+    c = scale.numel()
+    st = _lib().fpb200_bn_bwd_finalize(partials.data_ptr(), partials.shape[0], c, float(count),
+                                       scale.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(),
+                                       _ptr(dgamma), _ptr(dbeta), coef.data_ptr(), _stream())
+    capi.check(st, "bn_bwd_finalize", C=c)
+
+
+def bn_relu_bwd_apply(da, y, dy, scale, shift, coef) -> None:
+    dap, ldda = nhwc_view(da)
+    yp, ldy = nhwc_view(y)
+    dyp, lddy = nhwc_view(dy)
+    n, h, w, c = y.shape
+    st = _lib().fpb200_bn_relu_bwd_apply(dap, ldda, yp, ldy, dyp, lddy, scale.data_ptr(),
+                                         shift.data_ptr(), coef.data_ptr(), n * h * w, c, _stream())
+    capi.check(st, "bn_relu_bwd_apply", N=n, H=h, W=w, C=c)
+
+
+# ------------------------------------------------------------------------------------------
+def upsample2x_pad_concat_fwd(x, out) -> None:
+    """out (view [N,Ho,Wo,C]) <- zero-padded bilinear x2 (align_corners=True) of x [N,h,w,C]."""
+    xp, ldx = nhwc_view(x)
+    op, ldo = nhwc_view(out)
+    n, h, w, c = x.shape
+    ho, wo = out.shape[1], out.shape[2]
+    st = _lib().fpb200_upsample2x_pad_concat_fwd(xp, ldx, op, ldo, n, h, w, ho, wo, c, _stream())
+    capi.check(st, "upsample2x_pad_concat_fwd", N=n, h=h, w=w, Ho=ho, Wo=wo, C=c)
+
+
+def upsample2x_pad_concat_bwd(dout, dx) -> None:
+    dop, lddo = nhwc_view(dout)
+    dxp, lddx = nhwc_view(dx)
+    n, h, w, c = dx.shape
+    ho, wo = dout.shape[1], dout.shape[2]
+    st = _lib().fpb200_upsample2x_pad_concat_bwd(dop, lddo, dxp, lddx, n, h, w, ho, wo, c, _stream())
+    capi.check(st, "upsample2x_pad_concat_bwd", N=n, h=h, w=w, Ho=ho, Wo=wo, C=c)
+
+
+# ------------------------------------------------------------------------------------------
+def head1x1_fwd(x, w, b, logits) -> None:
+    xp, ldx = nhwc_view(x)
+    n, h, wd, c = x.shape
+    ncls = w.shape[0]
+    st = _lib().fpb200_head1x1_fwd(xp, ldx, w.data_ptr(), b.data_ptr(), logits.data_ptr(), n, h, wd, c,
+                                   ncls, _stream())
+    capi.check(st, "head1x1_fwd", N=n, H=h, W=wd, C=c, n_classes=ncls)
+
+
+def head1x1_bwd(dlogits, x, w, dx, dw, db, partials) -> None:
+    xp, ldx = nhwc_view(x)
+    dxp, lddx = nhwc_view(dx)
+    n, h, wd, c = x.shape
+    ncls = w.shape[0]
+    st = _lib().fpb200_head1x1_bwd(dlogits.data_ptr(), xp, ldx, w.data_ptr(), dxp, lddx, dw.data_ptr(),
+                                   db.data_ptr(), partials.data_ptr(), n, h, wd, c, ncls, _stream())
+    capi.check(st, "head1x1_bwd", N=n, H=h, W=wd, C=c, n_classes=ncls)
+
+
+def softmax_ce_argmax_fwd(logits, target, ignore_index, result, pred, confusion, partials) -> None:
+    n, ncls = logits.shape[0], logits.shape[1]
+    hw = logits.numel() // (n * ncls)
+    st = _lib().fpb200_softmax_ce_argmax_fwd(logits.data_ptr(), target.data_ptr(), int(ignore_index),
+                                             result.data_ptr(), _ptr(pred), _ptr(confusion),
+                                             partials.data_ptr(), n, ncls, hw, _stream())
+    capi.check(st, "softmax_ce_argmax_fwd", N=n, n_classes=ncls, hw=hw)
+
+
+def softmax_ce_bwd(logits, target, ignore_index, result, grad_out, dlogits) -> None:
+    n, ncls = logits.shape[0], logits.shape[1]
+    hw = logits.numel() // (n * ncls)
+    st = _lib().fpb200_softmax_ce_bwd(logits.data_ptr(), target.data_ptr(), int(ignore_index),
+                                      result.data_ptr(), _ptr(grad_out), dlogits.data_ptr(), n, ncls,
+                                      hw, _stream())
+    capi.check(st, "softmax_ce_bwd", N=n, n_classes=ncls, hw=hw)
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0) -> None:
+    st = _lib().fpb200_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
+                                 beta1, beta2, eps, step, grad_scale, _stream())
+    capi.check(st, "adam_step", n=p.numel())

@@ -1,0 +1,211 @@
+/*
+ * floodplanet_b200.h -- C ABI of the B200 (sm_100a) UNet hot path.
+ *
+ * This is the drop-in boundary for what `st_water_seg`'s UNet training / inference step
+ * dispatches to (reference: st_water_seg/models/unet.py, water_seg_model.py, ef_model.py).
+ * The reference has no FFI of its own -- every op below is a torch ATen call there -- so each
+ * entry point cites the reference line whose library dispatch it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless said
+ *     otherwise; `stream` is a cudaStream_t passed as void*.
+ *   - activations are NHWC bf16 "views": base pointer + pixel pitch `ld` (elements between
+ *     consecutive pixels), so a view can be a channel slice of a wider (concat) buffer.
+ *     Base pointers must be 16-byte aligned and `ld` a multiple of 8.
+ *   - no allocation, no host synchronisation, no global state: the caller owns workspaces.
+ *   - every function returns FPB200_OK (0) or a negative FPB200_ERR_* code; the Python host
+ *     side turns a non-zero status into RuntimeError(kernel name + shape).  There is no CPU
+ *     fallback anywhere behind this ABI.
+ */
+#ifndef FLOODPLANET_B200_H_
+#define FLOODPLANET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPB200_OK 0
+#define FPB200_ERR_SHAPE (-1)     /* unsupported / inconsistent dimensions            */
+#define FPB200_ERR_ALIGN (-2)     /* pointer or pitch alignment violated              */
+#define FPB200_ERR_LAUNCH (-3)    /* CUDA launch / runtime error (message on stderr)  */
+#define FPB200_ERR_DRIVER (-4)    /* driver entry point unavailable (no GPU driver)   */
+#define FPB200_ERR_TENSORMAP (-5) /* cuTensorMapEncodeTiled rejected the view         */
+
+/* library identification: returns the ABI version (bumped on any signature change). */
+int fpb200_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / ingest
+ * ---------------------------------------------------------------------------------------- */
+
+/* NCHW fp32 image(s) -> NHWC bf16 with channels zero-padded to `c_pad` (multiple of 8).
+ * Up to 8 source tensors are concatenated along C in the given order: this fuses
+ * EarlyFusionModel.forward's torch.concat chain (models/ef_model.py:24-47) and the implicit
+ * layout/cast step into one pass.  srcs / src_channels are HOST arrays of length n_src. */
+int fpb200_ingest_nchw_f32_to_nhwc_bf16(const float* const* srcs, const int* src_channels,
+                                        int n_src, void* dst, int c_pad, int N, int H, int W,
+                                        void* stream);
+
+/* Conv weight repack, OIHW fp32 [Cout][Cin][3][3] ->
+ *   fprop packing  bf16 [Cout][9][cin_pad]            (K-major GEMM B operand)
+ *   dgrad packing  bf16 [cin_pad_out][9][Cout]  with the filter rotated by 180 degrees
+ * Reference: nn.Conv2d parameters of DoubleConv (models/unet.py:14,16). */
+int fpb200_repack_weights_fprop(const float* w_oihw, void* w_packed, int Cout, int Cin,
+                                int cin_pad, void* stream);
+int fpb200_repack_weights_dgrad(const float* w_oihw, void* w_packed, int Cout, int Cin,
+                                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3x3 convolution (tcgen05 implicit GEMM)  -- models/unet.py:14,16 and their autograd
+ * ---------------------------------------------------------------------------------------- */
+
+/* rows of the BatchNorm partial-statistics workspace written by fprop: [rows][2][Cout] fp32 */
+int fpb200_conv_stat_rows(void);
+
+/* y = conv3x3(x, w) (no bias), bf16 NHWC in/out, fp32 accumulate.
+ *   Cin  multiple of 16 (channel-padded input), Cout multiple of 64.
+ *   scale/shift (nullable, [Cout]): epilogue y = acc*scale+shift, then ReLU if relu != 0
+ *     (eval-mode BatchNorm folded with the conv bias: models/unet.py:15,17 in .eval()).
+ *   stat_partials (nullable, [fpb200_conv_stat_rows()][2][Cout]): per-channel sum / sum of
+ *     squares of the fp32 accumulators (training-mode BatchNorm statistics, fused). */
+int fpb200_conv3x3_fprop_bf16_nhwc(const void* x, long ldx, const void* w_packed, void* y,
+                                   long ldy, int N, int H, int W, int Cin, int Cout,
+                                   const float* scale, const float* shift, int relu,
+                                   float* stat_partials, void* stream);
+
+/* dx = conv3x3_transpose(dy, w): Cout channels in, Cin (multiple of 64) channels out. */
+int fpb200_conv3x3_dgrad_bf16_nhwc(const void* dy, long lddy, const void* w_packed_dgrad,
+                                   void* dx, long lddx, int N, int H, int W, int Cout, int Cin,
+                                   void* stream);
+
+/* dW = sum_pixels dy (x) shifted x.  Two stages, deterministic:
+ *   stage 1 (tensor cores) writes split-K partials into `workspace`
+ *           (fp32, fpb200_conv3x3_wgrad_workspace_bytes(...) bytes),
+ *   stage 2 reduces them into dw_oihw fp32 [Cout][Cin_real][3][3] (overwrites). */
+long fpb200_conv3x3_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long lddy,
+                                   float* dw_oihw, void* workspace, int N, int H, int W,
+                                   int Cin, int cin_real, int Cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm2d + ReLU (+ MaxPool2d(2))  -- models/unet.py:15,17,29 and their autograd
+ * ---------------------------------------------------------------------------------------- */
+
+/* Reduce the fprop partials to batch statistics and fold them:
+ *   mean/var(biased) over `count` = N*H*W elements; invstd = rsqrt(var+eps)
+ *   scale = gamma*invstd, shift = beta - mean*scale           (apply pass coefficients)
+ *   save_mean/save_invstd kept for backward
+ *   running_mean = (1-m)*running_mean + m*(mean + conv_bias)  (conv bias is not in the GEMM;
+ *   running_var  = (1-m)*running_var  + m*var*count/(count-1)  it only shifts the mean)
+ * `num_partials` rows of [2][C] fp32. */
+int fpb200_bn_stats_finalize(const float* partials, int num_partials, int C, double count,
+                             const float* gamma, const float* beta, const float* conv_bias,
+                             float eps, float momentum, float* running_mean, float* running_var,
+                             float* scale, float* shift, float* save_mean, float* save_invstd,
+                             void* stream);
+
+/* eval-mode fold: scale = gamma/sqrt(running_var+eps), shift = beta + (bias-running_mean)*scale */
+int fpb200_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias,
+                        const float* running_mean, const float* running_var, float eps, int C,
+                        float* scale, float* shift, void* stream);
+
+/* a = relu(y*scale+shift) elementwise over an NHWC bf16 view. */
+int fpb200_bn_apply_relu(const void* y, long ldy, void* a, long lda, const float* scale,
+                         const float* shift, long num_pixels, int C, void* stream);
+
+/* Same, fused with MaxPool2d(2) (floor mode): writes the full-resolution activation `a`
+ * (nullable: pure pooling of an already activated input when scale == NULL), the pooled map
+ * `pooled` [N][H/2][W/2][C] and the window argmax (0..3, row-major in the 2x2 window, first
+ * maximum wins, NaN propagates -- torch's max_pool2d scan order) as one byte per element. */
+int fpb200_bn_apply_relu_maxpool2(const void* y, long ldy, void* a, long lda, void* pooled,
+                                  long ldp, uint8_t* pool_idx, const float* scale,
+                                  const float* shift, int N, int H, int W, int C, void* stream);
+
+/* MaxPool2d(2) backward fused with the skip-connection gradient add:
+ *   dx[n,h,w,c] = dskip[n,h,w,c] (nullable) + (pool_idx selects (h,w)) ? dpooled : 0 */
+int fpb200_maxpool2_bwd(const void* dpooled, long lddp, const uint8_t* pool_idx, const void* dskip,
+                        long ldds, void* dx, long lddx, int N, int H, int W, int C, void* stream);
+
+/* BatchNorm+ReLU backward, pass 1: with g = da * (y*scale+shift > 0) and
+ * xhat = (y-mean)*invstd, writes per-block partial sums of g and g*xhat:
+ * partials [fpb200_bn_bwd_rows()][2][C] fp32. */
+int fpb200_bn_bwd_rows(void);
+int fpb200_bn_relu_bwd_reduce(const void* da, long ldda, const void* y, long ldy,
+                              const float* scale, const float* shift, const float* save_mean,
+                              const float* save_invstd, float* partials, long num_pixels, int C,
+                              void* stream);
+/* pass 1b: reduce partials -> dgamma = sum(g*xhat), dbeta = sum(g) (fp32 [C], nullable) and
+ * the folded per-channel coefficients of pass 2, coef[2][C] = (P, Q):
+ *   dy = scale*(g - c1 - xhat*c2) = scale*g - P*y - Q,  c1 = sum(g)/count, c2 = sum(g*xhat)/count,
+ *   P = scale*c2*invstd, Q = scale*c1 - P*mean. */
+int fpb200_bn_bwd_finalize(const float* partials, int num_partials, int C, double count,
+                           const float* scale, const float* save_mean, const float* save_invstd,
+                           float* dgamma, float* dbeta, float* coef, void* stream);
+/* pass 2: dy = scale*g - P*y - Q with g = da * (y*scale+shift > 0), bf16 NHWC. */
+int fpb200_bn_relu_bwd_apply(const void* da, long ldda, const void* y, long ldy, void* dy,
+                             long lddy, const float* scale, const float* shift, const float* coef,
+                             long num_pixels, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Up: bilinear x2 (align_corners=True) + zero pad + concat  -- models/unet.py:43-45,54-66
+ * ---------------------------------------------------------------------------------------- */
+
+/* Writes up(x) zero-padded to (Ho, Wo) (pad_top = (Ho-2h)/2, pad_left = (Wo-2w)/2) into the
+ * NHWC view `out` (typically the second half of the concat buffer whose first half already
+ * holds the skip tensor: torch.cat([x2, x1], dim=1)). */
+int fpb200_upsample2x_pad_concat_fwd(const void* x, long ldx, void* out, long ldo, int N, int h,
+                                     int w, int Ho, int Wo, int C, void* stream);
+/* Gradient of the above w.r.t. x (gather form, deterministic): dx [N][h][w][C]. */
+int fpb200_upsample2x_pad_concat_bwd(const void* dout, long lddo, void* dx, long lddx, int N,
+                                     int h, int w, int Ho, int Wo, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * OutConv 1x1 head  -- models/unet.py:70-77
+ * ---------------------------------------------------------------------------------------- */
+
+/* logits[n,k,h,w] (fp32 NCHW) = sum_c x[n,h,w,c]*w[k,c] + b[k];  C = 64, n_classes <= 8. */
+int fpb200_head1x1_fwd(const void* x, long ldx, const float* w, const float* b, float* logits,
+                       int N, int H, int W, int C, int n_classes, void* stream);
+/* dx (bf16 NHWC), and per-block partials of dW [n_classes][C] and db [n_classes] in
+ * `partials` (fp32 [fpb200_head_bwd_rows()][n_classes*(C+1)]), reduced into dw/db. */
+int fpb200_head_bwd_rows(void);
+int fpb200_head1x1_bwd(const float* dlogits, const void* x, long ldx, const float* w, void* dx,
+                       long lddx, float* dw, float* db, float* partials, int N, int H, int W,
+                       int C, int n_classes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Masked cross-entropy + argmax (+ confusion counts)
+ *   -- models/water_seg_model.py:40,103-107 (nn.CrossEntropyLoss(ignore_index), argmax(dim=1))
+ * ---------------------------------------------------------------------------------------- */
+
+/* result (fp64 [4]):  [0] sum of -log softmax(logits)[t] over non-ignored pixels
+ *                     [1] number of non-ignored pixels   [2] number of invalid targets
+ *                     [3] mean loss = [0]/[1]  (NaN when [1] == 0, exactly like torch)
+ * pred (nullable, int64 [N][H][W]): argmax over classes, first maximum wins, NaN is maximal.
+ * confusion (nullable, int64 [n_classes][n_classes], row = target, col = pred; ignored pixels
+ * excluded) is ACCUMULATED into.  `partials` fp64 [fpb200_ce_rows()][4] workspace. */
+int fpb200_ce_rows(void);
+int fpb200_softmax_ce_argmax_fwd(const float* logits, const int64_t* target, long ignore_index,
+                                 double* result, int64_t* pred, int64_t* confusion,
+                                 double* partials, int N, int n_classes, long hw, void* stream);
+/* dlogits = (softmax - onehot) * (t != ignore) * grad_out / count; count = result[1].
+ * All-ignored batch (count == 0) gives zeros, matching nan_to_num'd reference behaviour. */
+int fpb200_softmax_ce_bwd(const float* logits, const int64_t* target, long ignore_index,
+                          const double* result, const float* grad_out, float* dlogits, int N,
+                          int n_classes, long hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser (water_seg_model.py:198-205, optim.Adam defaults) and misc
+ * ---------------------------------------------------------------------------------------- */
+
+/* One Adam step over a flat fp32 parameter slab (p, g, m, v all length n):
+ * torch.optim.Adam semantics (no amsgrad, no weight decay), grad pre-scaled by grad_scale. */
+int fpb200_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                     float beta2, float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOODPLANET_B200_H_ */

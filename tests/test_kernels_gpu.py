@@ -1,0 +1,390 @@
+"""Per-kernel parity tests (GPU): every C-ABI kernel against the torch op the reference
+dispatches to, on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): bit-exact for integer outputs (pool indices, argmax,
+confusion counts); <= 1e-2 relative for bf16-compute forward values; <= 2e-2 for gradients.
+Inputs are rounded to bf16 before the fp32 torch op runs, so the comparison isolates the
+kernel's own arithmetic (fp32 accumulate, one bf16 rounding on store).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from floodplanet_code_b200 import ops as _ops
+    return _ops
+
+
+def rel(a, b):
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+def rand_act(n, h, w, c, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(n, h, w, c, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+def rand_w(cout, cin, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    w = torch.randn(cout, cin, 3, 3, generator=g, device="cuda") / math.sqrt(9 * cin)
+    return w.to(torch.bfloat16).float()  # exactly representable in bf16
+
+
+CONV_SHAPES = [
+    # n, h, w, cin, cout
+    (2, 16, 16, 64, 64),
+    (1, 32, 32, 64, 128),
+    (2, 20, 24, 128, 256),     # ragged tiles
+    (1, 37, 37, 64, 64),       # odd size from the 300-px crop path
+    (2, 16, 16, 16, 64),       # first layer, KCH=16 (32B swizzle)
+    (1, 16, 24, 32, 64),       # early fusion pad 32 (64B swizzle)
+    (1, 8, 8, 512, 512),       # two N blocks, deep K
+    (1, 128, 128, 64, 64),     # wide rows: 1x128 tiles
+    (3, 18, 18, 256, 128),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES)
+def test_conv3x3_fprop_and_stats(ops, n, h, w, cin, cout):
+    x = rand_act(n, h, w, cin, 1)
+    wt = rand_w(cout, cin, 2)
+    wp = ops.repack_fprop(wt, cin)
+    y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    parts = torch.empty(ops.stat_rows(), 2, cout, dtype=torch.float32, device="cuda")
+    ops.conv3x3_fprop(x, wp, y, stat_partials=parts)
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(x.float()), wt, padding=1)
+    err = rel(nchw(y.float()), ref)
+    assert err < 1e-2, f"fprop rel err {err}"
+    s = parts.double().sum(0)
+    ref_sum = ref.double().sum((0, 2, 3))
+    ref_sq = (ref.double() ** 2).sum((0, 2, 3))
+    assert rel(s[0], ref_sum) < 2e-3 or float((s[0] - ref_sum).abs().max()) < 1e-2 * float(ref_sq.sqrt().max())
+    assert rel(s[1], ref_sq) < 2e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (1, 20, 24, 128, 256)])
+def test_conv3x3_fprop_affine_relu_into_concat_view(ops, n, h, w, cin, cout):
+    x = rand_act(n, h, w, cin, 3)
+    wt = rand_w(cout, cin, 4)
+    wp = ops.repack_fprop(wt, cin)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    scale = torch.rand(cout, generator=g, device="cuda") + 0.5
+    shift = torch.randn(cout, generator=g, device="cuda") * 0.2
+    buf = torch.full((n, h, w, 2 * cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3_fprop(x, wp, buf[..., :cout], scale=scale, shift=shift, relu=True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(nchw(x.float()), wt, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
+    assert rel(nchw(buf[..., :cout].float()), ref) < 1e-2
+    assert bool((buf[..., cout:] == 7.0).all()), "wrote outside the channel slice"
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (1, 20, 24, 128, 256), (1, 19, 19, 256, 64),
+                                            (1, 16, 16, 1024, 512)])
+def test_conv3x3_dgrad(ops, n, h, w, cin, cout):
+    dy = rand_act(n, h, w, cout, 6)
+    wt = rand_w(cout, cin, 7)
+    wd = ops.repack_dgrad(wt)
+    dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3_dgrad(dy, wd, dx)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt, nchw(dy.float()), padding=1)
+    err = rel(nchw(dx.float()), ref)
+    assert err < 2e-2, f"dgrad rel err {err}"
+
+
+WGRAD_SHAPES = [
+    # n, h, w, cin(padded), cin_real, cout
+    (2, 16, 16, 128, 128, 128),   # MODE_X_SHIFT, NB=2
+    (1, 24, 20, 64, 64, 128),     # MODE_X_SHIFT, NB=1
+    (2, 16, 16, 64, 64, 64),      # MODE_DY_SHIFT, 64
+    (2, 16, 16, 16, 4, 64),       # first layer (pad 16)
+    (1, 16, 16, 32, 21, 64),      # early fusion pad 32
+    (1, 37, 37, 128, 128, 64),    # odd size, Cout 64 / Cin 128
+    (3, 18, 18, 256, 256, 512),
+    (1, 64, 64, 64, 64, 64),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cin_real,cout", WGRAD_SHAPES)
+def test_conv3x3_wgrad(ops, n, h, w, cin, cin_real, cout):
+    x = rand_act(n, h, w, cin, 8)
+    if cin_real < cin:
+        x[..., cin_real:] = 0
+    dy = rand_act(n, h, w, cout, 9)
+    dw = torch.empty(cout, cin_real, 3, 3, dtype=torch.float32, device="cuda")
+    ws = torch.empty(ops.wgrad_workspace_bytes(n, h, w, cin, cout) // 4, dtype=torch.float32, device="cuda")
+    ops.conv3x3_wgrad(x, dy, dw, ws, cin_real)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(nchw(x.float())[:, :cin_real], (cout, cin_real, 3, 3), nchw(dy.float()),
+                                      padding=1)
+    err = rel(dw, ref)
+    assert err < 2e-3, f"wgrad rel err {err}"
+
+
+def test_wgrad_through_concat_view(ops):
+    n, h, w, c = 2, 16, 16, 64
+    buf = rand_act(n, h, w, 2 * c, 10)
+    dy = rand_act(n, h, w, 128, 11)
+    dw = torch.empty(128, 2 * c, 3, 3, dtype=torch.float32, device="cuda")
+    ws = torch.empty(ops.wgrad_workspace_bytes(n, h, w, 2 * c, 128) // 4, dtype=torch.float32, device="cuda")
+    ops.conv3x3_wgrad(buf, dy, dw, ws, 2 * c)
+    ref = torch.nn.grad.conv2d_weight(nchw(buf.float()), (128, 2 * c, 3, 3), nchw(dy.float()), padding=1)
+    assert rel(dw, ref) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------
+def test_ingest_early_fusion(ops):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    img = torch.rand(2, 4, 20, 24, generator=g, device="cuda")
+    dem = torch.rand(2, 1, 20, 24, generator=g, device="cuda")
+    s2 = torch.rand(2, 10, 20, 24, generator=g, device="cuda")
+    out = ops.ingest([img, dem, s2], 16)
+    ref = torch.cat([img, dem, s2], 1).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(out[..., :15], ref)
+    assert bool((out[..., 15:] == 0).all())
+
+
+def test_repack(ops):
+    wt = rand_w(64, 4, 1)
+    wp = ops.repack_fprop(wt, 16)
+    ref = torch.zeros(64, 9, 16, device="cuda")
+    ref[:, :, :4] = wt.permute(0, 2, 3, 1).reshape(64, 9, 4)
+    assert torch.equal(wp.float(), ref)
+    wt = rand_w(128, 64, 2)
+    wd = ops.repack_dgrad(wt)
+    ref = wt.flip(2, 3).permute(1, 2, 3, 0).reshape(64, 9, 128)
+    assert torch.equal(wd.float(), ref)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (1, 37, 37, 128), (2, 9, 75, 64)])
+def test_bn_train_forward_chain(ops, n, h, w, c):
+    """conv stats -> finalize -> apply+relu(+maxpool) against F.batch_norm/relu/max_pool2d."""
+    cin = 64
+    x = rand_act(n, h, w, cin, 12)
+    wt = rand_w(c, cin, 13)
+    g = torch.Generator(device="cuda").manual_seed(14)
+    gamma = torch.rand(c, generator=g, device="cuda") + 0.5
+    beta = torch.randn(c, generator=g, device="cuda") * 0.1
+    bias = torch.randn(c, generator=g, device="cuda") * 0.1
+    rm = torch.zeros(c, device="cuda")
+    rv = torch.ones(c, device="cuda")
+    y = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    parts = torch.empty(ops.stat_rows(), 2, c, device="cuda")
+    ops.conv3x3_fprop(x, ops.repack_fprop(wt, cin), y, stat_partials=parts)
+    scale, shift, mean, invstd = (torch.empty(c, device="cuda") for _ in range(4))
+    ops.bn_stats_finalize(parts, n * h * w, gamma, beta, bias, 1e-5, 0.1, rm, rv, scale, shift, mean, invstd)
+    a = torch.empty_like(y)
+    pooled = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device="cuda")
+    idx = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device="cuda")
+    ops.bn_apply_relu_maxpool2(y, a, pooled, idx, scale, shift)
+    a2 = torch.empty_like(y)
+    ops.bn_apply_relu(y, a2, scale, shift)
+    torch.cuda.synchronize()
+    # reference in fp32 from the same bf16 inputs
+    conv = F.conv2d(nchw(x.float()), wt, bias, padding=1)
+    rm_ref, rv_ref = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    ref = F.relu(F.batch_norm(conv, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5))
+    assert rel(rm, rm_ref) < 1e-3 and rel(rv, rv_ref) < 1e-3
+    assert rel(nchw(a.float()), ref) < 1e-2
+    assert torch.equal(a, a2)
+    # pooling: bit-exact against torch on the SAME (stored) pre-pool activation
+    pref, iref = F.max_pool2d(nchw(a.float()), 2, return_indices=True)
+    assert torch.equal(nchw(pooled.float()), pref)
+    ii = nchw(idx).long()
+    hh = torch.arange(h // 2, device="cuda")[None, None, :, None] * 2 + ii // 2
+    ww = torch.arange(w // 2, device="cuda")[None, None, None, :] * 2 + ii % 2
+    assert torch.equal(hh * w + ww, iref), "max-pool argmax differs from torch"
+
+
+def test_maxpool_ties_and_nan(ops):
+    a = torch.zeros(1, 4, 4, 8, dtype=torch.bfloat16, device="cuda")
+    a[0, 1, 1, 0] = float("nan")
+    a[0, 2, 3, 1] = 3.0
+    pooled = torch.empty(1, 2, 2, 8, dtype=torch.bfloat16, device="cuda")
+    idx = torch.empty(1, 2, 2, 8, dtype=torch.uint8, device="cuda")
+    ops.bn_apply_relu_maxpool2(a, None, pooled, idx, None, None)
+    pref, iref = F.max_pool2d(nchw(a.float()), 2, return_indices=True)
+    ii = nchw(idx).long()
+    hh = torch.arange(2, device="cuda")[None, None, :, None] * 2 + ii // 2
+    ww = torch.arange(2, device="cuda")[None, None, None, :] * 2 + ii % 2
+    assert torch.equal(hh * 4 + ww, iref)
+    assert torch.equal(torch.isnan(nchw(pooled.float())), torch.isnan(pref))
+    assert iref[0, 2].flatten().tolist() == [0, 2, 8, 10]  # all-zero window -> first element
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (1, 37, 37, 128)])
+def test_maxpool_bwd_with_skip(ops, n, h, w, c):
+    a = rand_act(n, h, w, c, 15)
+    pooled = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device="cuda")
+    idx = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device="cuda")
+    ops.bn_apply_relu_maxpool2(a, None, pooled, idx, None, None)
+    dp = rand_act(n, h // 2, w // 2, c, 16)
+    dcat = rand_act(n, h, w, 2 * c, 17)
+    dx = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    ops.maxpool2_bwd(dp, idx, dcat[..., :c], dx)
+    af = nchw(a.float()).requires_grad_(True)
+    F.max_pool2d(af, 2).backward(nchw(dp.float()))
+    ref = (af.grad + nchw(dcat[..., :c].float())).to(torch.bfloat16)
+    assert torch.equal(nchw(dx), ref)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (1, 19, 23, 256), (2, 8, 8, 512)])
+def test_bn_relu_backward(ops, n, h, w, c):
+    y = rand_act(n, h, w, c, 18)
+    da = rand_act(n, h, w, c, 19)
+    g = torch.Generator(device="cuda").manual_seed(20)
+    gamma = torch.rand(c, generator=g, device="cuda") + 0.5
+    beta = torch.randn(c, generator=g, device="cuda") * 0.3
+    yf = nchw(y.float()).requires_grad_(True)
+    gam = gamma.clone().requires_grad_(True)
+    bet = beta.clone().requires_grad_(True)
+    out = F.relu(F.batch_norm(yf, None, None, gam, bet, True, 0.1, 1e-5))
+    out.backward(nchw(da.float()))
+    mean = yf.detach().mean((0, 2, 3))
+    var = yf.detach().var((0, 2, 3), unbiased=False)
+    invstd = (var + 1e-5).rsqrt()
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    parts = torch.empty(ops.bn_bwd_rows(), 2, c, device="cuda")
+    ops.bn_relu_bwd_reduce(da, y, scale, shift, mean, invstd, parts)
+    dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    coef = torch.empty(2, c, device="cuda")
+    ops.bn_bwd_finalize(parts, n * h * w, scale, mean, invstd, dgamma, dbeta, coef)
+    dy = torch.empty_like(y)
+    ops.bn_relu_bwd_apply(da, y, dy, scale, shift, coef)
+    torch.cuda.synchronize()
+    assert rel(dgamma, gam.grad) < 2e-3
+    assert rel(dbeta, bet.grad) < 2e-3
+    assert rel(nchw(dy.float()), yf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("n,h,w,ho,wo,c", [(2, 8, 8, 16, 16, 64), (1, 18, 18, 37, 37, 128), (1, 1, 1, 2, 2, 64),
+                                           (1, 4, 5, 9, 10, 64)])
+def test_upsample_pad_concat(ops, n, h, w, ho, wo, c):
+    x = rand_act(n, h, w, c, 21)
+    cat = torch.zeros(n, ho, wo, 2 * c, dtype=torch.bfloat16, device="cuda")
+    ops.upsample2x_pad_concat_fwd(x, cat[..., c:])
+    xf = nchw(x.float()).requires_grad_(True)
+    up = F.interpolate(xf, scale_factor=2, mode="bilinear", align_corners=True)
+    dY, dX = ho - up.shape[2], wo - up.shape[3]
+    ref = F.pad(up, [dX // 2, dX - dX // 2, dY // 2, dY - dY // 2])
+    assert rel(nchw(cat[..., c:].float()), ref) < 5e-3
+    assert bool((cat[..., :c] == 0).all())
+    dcat = rand_act(n, ho, wo, 2 * c, 22)
+    dx = torch.empty_like(x)
+    ops.upsample2x_pad_concat_bwd(dcat[..., c:], dx)
+    ref.backward(nchw(dcat[..., c:].float()))
+    assert rel(nchw(dx.float()), xf.grad) < 5e-3
+
+
+def test_bilinear_align_corners_golden(ops):
+    # a 4 -> 8 row ramp maps to [0, 3/7, ..., 3]
+    x = torch.arange(4, dtype=torch.float32, device="cuda").view(1, 1, 4, 1).expand(1, 4, 4, 64)
+    x = x.contiguous().to(torch.bfloat16)  # value = column index w
+    out = torch.empty(1, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    ops.upsample2x_pad_concat_fwd(x, out)
+    want = torch.tensor([i * 3 / 7 for i in range(8)], device="cuda")
+    assert torch.allclose(out[0, 0, :, 0].float(), want, rtol=4e-3, atol=0)
+    assert float(out[0, 0, 0, 0]) == 0.0 and float(out[0, 0, 7, 0]) == 3.0
+
+
+@pytest.mark.parametrize("ncls", [2, 3])
+def test_head_fwd_bwd(ops, ncls):
+    n, h, w, c = 2, 20, 24, 64
+    x = rand_act(n, h, w, c, 23)
+    g = torch.Generator(device="cuda").manual_seed(24)
+    wt = torch.randn(ncls, c, generator=g, device="cuda") / 8
+    b = torch.randn(ncls, generator=g, device="cuda")
+    logits = torch.empty(n, ncls, h, w, device="cuda")
+    ops.head1x1_fwd(x, wt, b, logits)
+    xf = nchw(x.float()).requires_grad_(True)
+    wr = wt.clone().view(ncls, c, 1, 1).requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv2d(xf, wr, br)
+    assert rel(logits, ref) < 1e-5
+    dl = torch.randn(n, ncls, h, w, generator=g, device="cuda")
+    ref.backward(dl)
+    dx = torch.empty_like(x)
+    dw = torch.empty(ncls, c, device="cuda")
+    db = torch.empty(ncls, device="cuda")
+    parts = torch.empty(ops.head_bwd_rows(), ncls * (c + 1), device="cuda")
+    ops.head1x1_bwd(dl, x, wt, dx, dw, db, parts)
+    assert rel(nchw(dx.float()), xf.grad) < 1e-2
+    assert rel(dw, wr.grad.view(ncls, c)) < 1e-4
+    assert rel(db, br.grad) < 1e-4
+
+
+def _ce(ops, logits, target, ignore_index):
+    n, ncls = logits.shape[:2]
+    result = torch.empty(4, dtype=torch.float64, device="cuda")
+    pred = torch.empty(target.shape, dtype=torch.int64, device="cuda")
+    conf = torch.zeros(ncls, ncls, dtype=torch.int64, device="cuda")
+    parts = torch.empty(ops.ce_rows(), 4, dtype=torch.float64, device="cuda")
+    ops.softmax_ce_argmax_fwd(logits, target, ignore_index, result, pred, conf, parts)
+    dl = torch.empty_like(logits)
+    go = torch.ones((), device="cuda")
+    ops.softmax_ce_bwd(logits, target, ignore_index, result, go, dl)
+    torch.cuda.synchronize()
+    return result, pred, conf, dl
+
+
+def test_masked_ce_argmax(ops):
+    g = torch.Generator(device="cuda").manual_seed(25)
+    n, ncls, h, w = 3, 3, 33, 47
+    logits = torch.randn(n, ncls, h, w, generator=g, device="cuda") * 3
+    target = (torch.rand(n, h, w, generator=g, device="cuda") < 0.42).long()
+    result, pred, conf, dl = _ce(ops, logits, target, 0)
+    lr = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, target, ignore_index=0)
+    ref.backward()
+    assert abs(float(result[3]) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert int(result[1]) == int((target != 0).sum())
+    assert torch.equal(pred, logits.argmax(1))
+    assert rel(dl, lr.grad) < 1e-5
+    m = target != 0
+    want = torch.zeros(ncls, ncls, dtype=torch.int64, device="cuda")
+    want.index_put_((target[m], logits.argmax(1)[m]), torch.ones((), dtype=torch.int64, device="cuda"), accumulate=True)
+    assert torch.equal(conf, want)
+
+
+def test_ce_all_ignored_and_ties(ops):
+    logits = torch.zeros(1, 3, 4, 4, device="cuda")  # ties -> class 0
+    logits[0, :, 0, 0] = torch.tensor([1.0, float("nan"), 2.0])
+    target = torch.zeros(1, 4, 4, dtype=torch.int64, device="cuda")
+    result, pred, conf, dl = _ce(ops, logits, target, 0)
+    assert math.isnan(float(result[3]))        # torch: mean over empty set -> NaN
+    assert bool((dl == 0).all())               # ... and zero grads after nan_to_num
+    assert torch.equal(pred, logits.argmax(1))  # ties -> lowest index, NaN maximal
+    assert int(conf.sum()) == 0
+
+
+def test_adam_matches_torch(ops):
+    g = torch.Generator(device="cuda").manual_seed(26)
+    p = torch.randn(10007, generator=g, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-4)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn(10007, generator=g, device="cuda")
+        pr.grad = gr.clone()
+        opt.step()
+        ops.adam_step(p, gr, m, v, 1e-4, 0.9, 0.999, 1e-8, step)
+    assert rel(p, pr.detach()) < 1e-6

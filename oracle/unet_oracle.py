@@ -1,0 +1,186 @@
+"""ORACLE -- test infrastructure only, never a product path.
+
+A CPU/fp32 restatement of the reference algorithm for the UNet hot path, written functionally
+over a ``state_dict`` with the reference's keys.  Only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may import this module, and only
+as the checker or the reported baseline.  The product (``floodplanet_code_b200``) never
+imports it and fails loudly without its CUDA library.
+
+All arithmetic lives in torch ATen ops, exactly as in the reference (a pure-PyTorch project,
+torch pinned at 1.10.2 in environment.yml:114; the op semantics used here are unchanged in the
+installed torch 2.11).  Each function cites the reference lines it restates:
+
+  conv3x3+BN+ReLU x2      st_water_seg/models/unet.py:6-20      (DoubleConv)
+  maxpool2 + DoubleConv   st_water_seg/models/unet.py:23-32     (Down)
+  up x2 + pad + cat + DC  st_water_seg/models/unet.py:35-67     (Up, bilinear branch)
+  1x1 head                st_water_seg/models/unet.py:70-77     (OutConv)
+  wiring                  st_water_seg/models/unet.py:80-111    (UNet.__init__/forward)
+  early-fusion concat     st_water_seg/models/ef_model.py:24-47
+  loss / NaN guard / pred st_water_seg/models/water_seg_model.py:40,98-107
+  Adam                    st_water_seg/models/water_seg_model.py:198-205
+
+Pinning: the reference ships no tests or golden vectors, so the oracle is
+pinned against the REFERENCE ITSELF, imported by file path in the build container, by
+``tests/golden/make_golden.py``; the resulting fixtures are committed under ``tests/golden/``
+and re-checked by ``tests/test_oracle.py`` (CPU).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+EXTRA_KEYS = ('dem', 'slope', 'preflood', 'pre_post_difference', 'hand')  # ef_model.py:27-41
+
+# (prefix of the DoubleConv's nn.Sequential, cin, mid, cout)  -- unet.py:88-97 with bilinear=True
+def _double_convs(n_channels: int) -> List[Tuple[str, int, int, int]]:
+    return [
+        ("inc.double_conv", n_channels, 64, 64),
+        ("down1.maxpool_conv.1.double_conv", 64, 128, 128),
+        ("down2.maxpool_conv.1.double_conv", 128, 256, 256),
+        ("down3.maxpool_conv.1.double_conv", 256, 512, 512),
+        ("down4.maxpool_conv.1.double_conv", 512, 512, 512),
+        ("up1.conv.double_conv", 1024, 512, 256),
+        ("up2.conv.double_conv", 512, 256, 128),
+        ("up3.conv.double_conv", 256, 128, 64),
+        ("up4.conv.double_conv", 128, 64, 64),
+    ]
+
+
+def init_state_dict(n_channels: int, n_classes: int, seed: Optional[int] = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Fresh parameters with the reference's default initialisation, consuming the RNG in the
+    same order as ``UNet.__init__`` (unet.py:82-98): per DoubleConv conv/bn/conv/bn, then the
+    head -- so ``torch.manual_seed(s); UNet(...)`` in the reference gives identical tensors."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for prefix, cin, mid, cout in _double_convs(n_channels):
+        for idx, (ci, co) in ((0, (cin, mid)), (3, (mid, cout))):
+            conv = nn.Conv2d(ci, co, kernel_size=3, padding=1)
+            bn = nn.BatchNorm2d(co)
+            sd[f"{prefix}.{idx}.weight"] = conv.weight.detach().clone()
+            sd[f"{prefix}.{idx}.bias"] = conv.bias.detach().clone()
+            for k, v in bn.state_dict().items():
+                sd[f"{prefix}.{idx + 1}.{k}"] = v.detach().clone()
+    head = nn.Conv2d(64, n_classes, kernel_size=1)
+    sd["outc.conv.weight"] = head.weight.detach().clone()
+    sd["outc.conv.bias"] = head.bias.detach().clone()
+    return sd
+
+
+def trainable_keys(sd: Dict[str, torch.Tensor]) -> List[str]:
+    return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var")
+                                  or k.endswith("num_batches_tracked"))]
+
+
+def _conv_bn_relu(x, sd, conv, bn, training: bool):
+    """unet.py:14-17 -- Conv2d(k=3,p=1,bias) -> BatchNorm2d(eps=1e-5, momentum=0.1) -> ReLU."""
+    x = F.conv2d(x, sd[f"{conv}.weight"], sd[f"{conv}.bias"], padding=1)
+    if training:
+        sd[f"{bn}.num_batches_tracked"] += 1
+    x = F.batch_norm(x, sd[f"{bn}.running_mean"], sd[f"{bn}.running_var"], sd[f"{bn}.weight"],
+                     sd[f"{bn}.bias"], training, 0.1, 1e-5)
+    return F.relu(x)
+
+
+def _double_conv(x, sd, prefix, training):
+    x = _conv_bn_relu(x, sd, f"{prefix}.0", f"{prefix}.1", training)
+    return _conv_bn_relu(x, sd, f"{prefix}.3", f"{prefix}.4", training)
+
+
+def _up(x1, x2, sd, prefix, training):
+    """unet.py:54-67 -- bilinear x2 (align_corners=True), zero-pad to the skip size with the
+    smaller half on the left/top, cat([skip, upsampled]) along C, DoubleConv."""
+    x1 = F.interpolate(x1, scale_factor=2, mode='bilinear', align_corners=True)
+    dy = x2.size(2) - x1.size(2)
+    dx = x2.size(3) - x1.size(3)
+    x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    return _double_conv(torch.cat([x2, x1], dim=1), sd, prefix, training)
+
+
+def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True,
+                 return_features: bool = False):
+    """unet.py:100-111.  ``sd`` BN buffers are updated in place when ``training``."""
+    x1 = _double_conv(x, sd, "inc.double_conv", training)
+    x2 = _double_conv(F.max_pool2d(x1, 2), sd, "down1.maxpool_conv.1.double_conv", training)
+    x3 = _double_conv(F.max_pool2d(x2, 2), sd, "down2.maxpool_conv.1.double_conv", training)
+    x4 = _double_conv(F.max_pool2d(x3, 2), sd, "down3.maxpool_conv.1.double_conv", training)
+    x5 = _double_conv(F.max_pool2d(x4, 2), sd, "down4.maxpool_conv.1.double_conv", training)
+    u = _up(x5, x4, sd, "up1.conv.double_conv", training)
+    u = _up(u, x3, sd, "up2.conv.double_conv", training)
+    u = _up(u, x2, sd, "up3.conv.double_conv", training)
+    u = _up(u, x1, sd, "up4.conv.double_conv", training)
+    logits = F.conv2d(u, sd["outc.conv.weight"], sd["outc.conv.bias"])
+    if return_features:
+        return logits, [x1, x2, x3, x4, x5]
+    return logits
+
+
+def early_fusion_input(batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """ef_model.py:24-44 -- image then dem, slope, preflood, pre_post_difference, hand."""
+    images = batch['image']
+    for k in EXTRA_KEYS:
+        if k in batch:
+            images = torch.concat([images, batch[k]], dim=1)
+    return images
+
+
+def masked_ce(logits: torch.Tensor, target: torch.Tensor, ignore_index: Optional[int]):
+    """water_seg_model.py:40,103-107 -- CE(mean over non-ignored), NaN -> 0, argmax(dim=1)."""
+    ii = -100 if ignore_index is None else ignore_index
+    loss = F.cross_entropy(logits, target, ignore_index=ii)
+    if torch.isnan(loss):
+        loss = torch.nan_to_num(loss)
+    return loss, logits.argmax(dim=1)
+
+
+def training_step(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor],
+                  ignore_index: Optional[int], early_fusion: bool = True):
+    """Forward + loss + backward of one reference training step (water_seg_model.py:98-136 and
+    the ``loss.backward()`` Lightning runs).  Returns (loss, pred, logits, {name: grad})."""
+    keys = trainable_keys(sd)
+    for k in keys:
+        sd[k].requires_grad_(True)
+        sd[k].grad = None
+    x = early_fusion_input(batch) if early_fusion else batch['image']
+    logits = unet_forward(sd, x, training=True)
+    loss, pred = masked_ce(logits, batch['target'], ignore_index)
+    loss.backward()
+    grads = {k: (sd[k].grad.detach().clone() if sd[k].grad is not None else torch.zeros_like(sd[k]))
+             for k in keys}
+    for k in keys:
+        sd[k].requires_grad_(False)
+        sd[k].grad = None
+    return loss.detach(), pred, logits.detach(), grads
+
+
+def confusion_counts(pred: torch.Tensor, target: torch.Tensor, n_classes: int,
+                     ignore_index: Optional[int]) -> torch.Tensor:
+    keep = torch.ones_like(target, dtype=torch.bool) if ignore_index is None else target != ignore_index
+    idx = target[keep] * n_classes + pred[keep]
+    return torch.bincount(idx, minlength=n_classes * n_classes).view(n_classes, n_classes)
+
+
+def micro_metrics(conf: torch.Tensor) -> Dict[str, float]:
+    """torchmetrics multiclass micro F1 / Jaccard / Accuracy with ignore_index
+    (water_seg_model.py:46-63) expressed on confusion counts."""
+    conf = conf.double()
+    tp, total = conf.diagonal().sum(), conf.sum()
+    acc = float(torch.nan_to_num(tp / total))
+    return {"F1": acc, "Accuracy": acc, "Jaccard": float(torch.nan_to_num(tp / (2 * total - tp)))}
+
+
+def synthetic_batch(n: int, c: int, h: int, w: int, seed: int = 0, ignore_frac: float = 0.58,
+                    block: int = 32, device: str = "cpu") -> Dict[str, torch.Tensor]:
+    """image ~ U[0,1) f32; int64 target, spatially blocky, ~58% class 0
+    (ignored under the default config) / 42% class 1, never class 2."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    image = torch.rand(n, c, h, w, generator=g)
+    hb, wb = (h + block - 1) // block, (w + block - 1) // block
+    coarse = torch.rand(n, 1, hb, wb, generator=g)
+    field = F.interpolate(coarse, size=(hb * block, wb * block), mode="nearest")[:, 0, :h, :w]
+    target = (field >= ignore_frac).long()
+    return {"image": image.to(device), "target": target.to(device)}

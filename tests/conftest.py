@@ -13,6 +13,10 @@ os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
+    # the torch ops used as the checker must be true fp32 (no TF32 tensor-core shortcuts)
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def pytest_collection_modifyitems(config, items):

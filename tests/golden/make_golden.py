@@ -1,0 +1,134 @@
+"""Generate the committed golden fixtures from the REFERENCE ITSELF.
+
+Runs only in the build container, where the reference checkout exists at /root/reference:
+imports ``st_water_seg/models/unet.py`` and ``st_water_seg/datasets/utils.py`` by file path
+(the package import needs pytorch_lightning / hydra, which are not installed), runs them on
+CPU fp32 with fixed seeds and stores small input/output vectors in ``tests/golden/*.pt``.
+The GPU box has no /root/reference; tests there read only the fixtures.
+
+    python tests/golden/make_golden.py
+"""
+import importlib.util
+import sys
+import types
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+
+REF = Path("/root/reference/st_water_seg")
+OUT = Path(__file__).resolve().parent
+
+
+def load_by_path(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def summarize_grads(named_grads):
+    out = {}
+    for k, g in named_grads.items():
+        g = g.detach().double().flatten()
+        out[k] = {"norm": float(g.norm()), "sum": float(g.sum()), "head": g[:8].float().clone()}
+    return out
+
+
+def unet_case(ref_unet, name, n, c, h, w, n_classes, ignore_index, seed, extra=None, block=8):
+    sys.path.insert(0, str(OUT.parent.parent))
+    from oracle import unet_oracle as O
+    torch.manual_seed(seed)
+    model = ref_unet.UNet(c, n_classes)
+    init_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = O.synthetic_batch(n, c, h, w, seed=seed + 1, block=block)
+    if extra == "all_ignored":
+        batch["target"].zero_()
+    model.train()
+    logits = model(batch["image"])
+    loss = nn.CrossEntropyLoss(ignore_index=ignore_index)(logits, batch["target"])
+    if torch.isnan(loss):
+        loss = torch.nan_to_num(loss)
+    pred = logits.argmax(dim=1)
+    loss.backward()
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+    after = model.state_dict()
+    model.eval()
+    with torch.no_grad():
+        logits_eval = model(batch["image"])
+    fx = {
+        "cfg": dict(n=n, c=c, h=h, w=w, n_classes=n_classes, ignore_index=ignore_index, seed=seed),
+        "init_checksum": {k: float(v.double().sum()) for k, v in init_sd.items()},
+        "image": batch["image"], "target": batch["target"],
+        "logits_train": logits.detach().clone(), "loss": float(loss.detach()), "pred": pred.clone(),
+        "grads": summarize_grads(grads),
+        "grad_full": {k: grads[k].detach().clone() for k in
+                      ("inc.double_conv.0.weight", "outc.conv.weight", "outc.conv.bias",
+                       "inc.double_conv.1.weight", "inc.double_conv.1.bias",
+                       "up4.conv.double_conv.4.weight", "up4.conv.double_conv.3.bias")},
+        "bn_after": {k: after[k].clone() for k in after if k.startswith("inc.double_conv.1.")
+                     or k.startswith("down4.maxpool_conv.1.double_conv.4.")},
+        "logits_eval": logits_eval.clone(),
+    }
+    torch.save(fx, OUT / f"{name}.pt")
+    print(name, "loss", float(loss.detach()), "ignored_frac", float((batch["target"] == 0).float().mean()), "bytes", (OUT / f"{name}.pt").stat().st_size)
+
+
+def op_semantics_case():
+    """Edge semantics of the third-party ops the path relies on."""
+    import torch.nn.functional as F
+    fx = {}
+    z = torch.zeros(1, 1, 4, 4)
+    _, idx = F.max_pool2d(z, 2, return_indices=True)
+    fx["maxpool_zero_idx"] = idx.flatten().tolist()
+    zn = z.clone(); zn[0, 0, 1, 1] = float("nan")
+    p, idx = F.max_pool2d(zn, 2, return_indices=True)
+    fx["maxpool_nan_idx"] = idx.flatten().tolist()
+    fx["maxpool_nan_isnan"] = torch.isnan(p).flatten().tolist()
+    lg = torch.zeros(1, 3, 2, 2)
+    lg[0, :, 0, 0] = torch.tensor([1.0, float("nan"), 2.0])
+    fx["argmax_ties"] = lg.argmax(1).flatten().tolist()
+    t0 = torch.zeros(1, 2, 2, dtype=torch.long)
+    lgr = torch.randn(1, 3, 2, 2, requires_grad=True)
+    l = F.cross_entropy(lgr, t0, ignore_index=0)
+    fx["ce_all_ignored_isnan"] = bool(torch.isnan(l))
+    torch.nan_to_num(l).backward()
+    fx["ce_all_ignored_grad_abs_sum"] = float(lgr.grad.abs().sum())
+    ramp = torch.arange(4.0).view(1, 1, 1, 4)
+    fx["bilinear_4_to_8"] = F.interpolate(ramp, scale_factor=(1, 2), mode="bilinear", align_corners=True).flatten()
+    x = torch.randn(4, 2, 3, 3, generator=torch.Generator().manual_seed(0))
+    rm, rv = torch.zeros(2), torch.ones(2)
+    F.batch_norm(x, rm, rv, None, None, True, 0.1, 1e-5)
+    fx["bn_x"] = x
+    fx["bn_running_mean"] = rm
+    fx["bn_running_var"] = rv
+    torch.save(fx, OUT / "op_semantics.pt")
+    print("op_semantics", fx["maxpool_zero_idx"], fx["argmax_ties"])
+
+
+def tiler_case():
+    hydra = types.ModuleType("hydra"); hydra.utils = types.ModuleType("hydra.utils")
+    hydra.utils.get_original_cwd = lambda: "."
+    sys.modules.setdefault("hydra", hydra); sys.modules.setdefault("hydra.utils", hydra.utils)
+    ref_utils = load_by_path("ref_ds_utils", REF / "datasets" / "utils.py")
+    cases = [(10240, 10240, 512, 512, 512), (10240, 10240, 512, 512, 256), (1024, 1024, 300, 300, 150),
+             (700, 530, 300, 300, 300), (1000, 900, 512, 512, 512)]
+    fx = {}
+    for (H, W, ch, cw, st) in cases:
+        sl = ref_utils.get_crop_slices(H, W, ch, cw, st, mode="exact")
+        fx[(H, W, ch, cw, st)] = {"count": len(sl), "head": sl[:5], "tail": sl[-5:],
+                                  "checksum": int(sum((i + 1) * (a + 3 * b + 5 * c + 7 * d)
+                                                      for i, (a, b, c, d) in enumerate(sl)))}
+    torch.save(fx, OUT / "tiler.pt")
+    print("tiler", {k: v["count"] for k, v in fx.items()})
+
+
+if __name__ == "__main__":
+    ref_unet = load_by_path("ref_unet", REF / "models" / "unet.py")
+    unet_case(ref_unet, "unet_c4_32", n=2, c=4, h=32, w=32, n_classes=3, ignore_index=0, seed=0)
+    unet_case(ref_unet, "unet_c4_44x36", n=1, c=4, h=44, w=36, n_classes=3, ignore_index=0, seed=3)
+    unet_case(ref_unet, "unet_c6_37_ef", n=2, c=6, h=37, w=37, n_classes=2, ignore_index=-100, seed=5)
+    unet_case(ref_unet, "unet_c4_32_allignored", n=1, c=4, h=32, w=32, n_classes=3, ignore_index=0, seed=7,
+              extra="all_ignored")
+    op_semantics_case()
+    tiler_case()

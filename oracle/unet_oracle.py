@@ -76,8 +76,41 @@ def trainable_keys(sd: Dict[str, torch.Tensor]) -> List[str]:
                                   or k.endswith("num_batches_tracked"))]
 
 
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _conv_bn_relu_bf16(x, sd, conv, bn, training: bool):
+    """Same layer with the CUDA path's storage precision emulated (NOT the reference's
+    arithmetic -- a diagnostic that separates kernel bugs from bf16 rounding): bf16 conv
+    operands, fp32 accumulation, statistics from the fp32 accumulators, normalisation applied
+    to the bf16-stored conv output, bf16-stored activation.  The conv bias only shifts the
+    batch mean, so it is kept out of the GEMM exactly like the kernels do."""
+    y = F.conv2d(x, _bf16(sd[f"{conv}.weight"]), None, padding=1)
+    if training:
+        sd[f"{bn}.num_batches_tracked"] += 1
+        mean = y.mean((0, 2, 3))
+        var = y.var((0, 2, 3), unbiased=False)
+        n = y.numel() / y.shape[1]
+        with torch.no_grad():
+            sd[f"{bn}.running_mean"].mul_(0.9).add_(0.1 * (mean + sd[f"{conv}.bias"]))
+            sd[f"{bn}.running_var"].mul_(0.9).add_(0.1 * var * n / max(n - 1, 1))
+        scale = sd[f"{bn}.weight"] * torch.rsqrt(var + 1e-5)
+        shift = sd[f"{bn}.bias"] - mean * scale
+        y = _bf16(y)
+    else:
+        scale = sd[f"{bn}.weight"] / torch.sqrt(sd[f"{bn}.running_var"] + 1e-5)
+        shift = sd[f"{bn}.bias"] + (sd[f"{conv}.bias"] - sd[f"{bn}.running_mean"]) * scale
+    return _bf16(F.relu(y * scale[None, :, None, None] + shift[None, :, None, None]))
+
+
+_EMULATE_BF16 = False
+
+
 def _conv_bn_relu(x, sd, conv, bn, training: bool):
     """unet.py:14-17 -- Conv2d(k=3,p=1,bias) -> BatchNorm2d(eps=1e-5, momentum=0.1) -> ReLU."""
+    if _EMULATE_BF16:
+        return _conv_bn_relu_bf16(x, sd, conv, bn, training)
     x = F.conv2d(x, sd[f"{conv}.weight"], sd[f"{conv}.bias"], padding=1)
     if training:
         sd[f"{bn}.num_batches_tracked"] += 1
@@ -98,7 +131,21 @@ def _up(x1, x2, sd, prefix, training):
     dy = x2.size(2) - x1.size(2)
     dx = x2.size(3) - x1.size(3)
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    if _EMULATE_BF16:
+        x1 = _bf16(x1)
     return _double_conv(torch.cat([x2, x1], dim=1), sd, prefix, training)
+
+
+def unet_forward_bf16_emulated(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True):
+    """Diagnostic variant of :func:`unet_forward` with the CUDA path's bf16 storage points
+    emulated (see :func:`_conv_bn_relu_bf16`).  The CUDA path must match THIS to ~1e-3; the
+    distance between this and the fp32 reference is pure bf16 rounding, not a kernel error."""
+    global _EMULATE_BF16
+    _EMULATE_BF16 = True
+    try:
+        return unet_forward(sd, _bf16(x), training)
+    finally:
+        _EMULATE_BF16 = False
 
 
 def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True,

@@ -1,115 +1,127 @@
-// 3x3 / pad 1 / stride 1 convolution as an implicit GEMM on the sm_100a tensor cores.
+// 3x3 / pad 1 / stride 1 convolution as an implicit GEMM on the sm_100a tensor cores,
+// "halo" formulation.
 //
 // Replaces what nn.Conv2d(k=3, padding=1) dispatches to in the reference
 // (st_water_seg/models/unet.py:14,16) -- forward (fprop) and, with the transposed +
 // rotated weight packing, the data gradient (dgrad, the autograd of the same line).
 //
 //   D[m, co] = sum_{tap, ci} A[m + tap, ci] * Wp[co, tap, ci]
-//     m   = output pixel (n, h, w)            GEMM M = N*H*W, tiled 128 pixels = TH x TW patch
-//     co  = output channel                    GEMM N = Cout,  tiled BN
-//     tap = (r, s) in 3x3, ci = input chan.   GEMM K = 9*Cin, tiled KCH per pipeline stage
 //
-// Data movement: activations are NHWC bf16.  For every (tap, channel chunk) the TMA unit
-// fetches the shifted TH x TW x KCH box straight into 128B/64B/32B-swizzled shared memory;
-// the 1-pixel halo of the conv is the TMA out-of-bounds zero fill, so no im2col buffer and
-// no boundary branches exist anywhere.  Weights [Cout][9*Cin] are a plain K-major matrix.
+// Work item of a CTA: a 16x16 pixel patch of one image (= two 128-row MMA tiles, the left
+// and right 16x8 halves) x BN output channels.  For every 64-channel chunk of the input the
+// TMA unit fetches ONE (16+2) x (16+2) x KCH box -- the patch plus its 1-pixel halo, zero
+// filled outside the image -- into swizzled shared memory, one 128-byte row per pixel.  All
+// nine filter taps and both MMA tiles then read that single box: a tap shift (r, s) is just
+// a different start address (r*18 + s rows further) in the tcgen05 shared-memory descriptor,
+// and the 8-row core-matrix groups of a tile are one image row each, a constant 18 rows
+// apart (descriptor stride).  (Measured on B200: the 128B/64B/32B swizzle is a function of
+// the absolute shared-memory address, so operand start addresses that are only 128-byte --
+// not 1024-byte -- aligned read back exactly what TMA wrote, with descriptor base_offset 0.)  Activation traffic into the SM drops from 9 boxes per chunk to
+// 1.27 (halo overhead) and every weight tile [BN x KCH] is used by two MMA tiles, which is
+// what lifts the kernel from smem-fill bound to tensor-pipe bound.
 //
-// Execution: persistent CTAs (one per SM), warp specialised:
-//   warp 0    TMA producer           (one elected lane)
-//   warp 1    tcgen05.mma issuer     (one elected lane) + TMEM allocator
-//   warps 2-5 epilogue: tcgen05.ld accumulator -> registers -> fused epilogue -> global
-// Accumulators live in TMEM, double buffered (2 x BN fp32 columns), so the epilogue of
-// tile i overlaps the MMAs of tile i+1.
+// Pipeline: persistent CTAs (one per SM), warp specialised
+//   warp 0    TMA producer: ring A (activation boxes), ring B (weight tiles per tap)
+//   warp 1    tcgen05.mma issuer + TMEM allocator
+//   warps 2-5 epilogue: tcgen05.ld -> registers -> fused epilogue -> global
+// TMEM holds 2 (double buffer) x 2 (tiles) x BN fp32 accumulator columns, so the epilogue
+// of one patch overlaps the MMAs of the next.
 //
 // Fused epilogues (runtime flags, warp-uniform):
-//   * per-channel affine (+ReLU): eval-mode BatchNorm folded to scale/shift, or bias add
-//   * BatchNorm batch-statistic partials: per-channel sum and sum of squares of the fp32
-//     accumulators, reduced over the 32 rows of each warp with a shuffle transpose-reduce
-//     and accumulated in registers across all tiles of the persistent CTA
-//   * bf16 cast + 16-byte vector stores into an NHWC view with an arbitrary pixel pitch
-//     (so the output can land directly inside a concat buffer).
+//   * per-channel affine (+ReLU): eval-mode BatchNorm folded to scale/shift
+//   * BatchNorm batch-statistic partials: per-channel sum / sum of squares of the fp32
+//     accumulators (shuffle transpose-reduce per warp, accumulated across the CTA's patches)
+//   * bf16 cast + 16-byte stores into an NHWC view with arbitrary pixel pitch.
 #include "host_common.h"
 #include "ptx.cuh"
 
 namespace fp {
+namespace v1 {
+int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, long ldy, int N, int H,
+                     int W, int Cin, int Cout, const float* scale, const float* shift, int relu,
+                     float* stat_partials, cudaStream_t stream);
+}
 
-struct ConvParams {
+static int g_conv_impl = 2;     // bring-up switch (debug hook below): 1 = per-tap kernel
+
+struct HaloParams {
   int N, H, W;
   int Cin;   // padded input channels (multiple of KCH)
   int Cout;  // multiple of BN
-  int tw_log2;
-  int tiles_w, tiles_h;
-  int num_m_tiles, num_n_blks;
+  int patches_w, patches_h;
+  int num_patches, num_n_blks;
   __nv_bfloat16* y;
   long ldy;
-  const float* scale;  // nullable
-  const float* shift;  // nullable
+  const float* scale;
+  const float* shift;
   int relu;
-  float* stat_partials;  // nullable; [gridDim.x*4][2][Cout]
+  float* stat_partials;  // [gridDim.x*4][2][Cout]
 };
 
-constexpr int kBM = 128;
-constexpr int kNumThreads = 192;
+constexpr int kPatch = 16;        // patch edge in pixels
+constexpr int kBox = kPatch + 2;  // with halo
+constexpr int kBoxRows = kBox * kBox;
+constexpr int kHaloThreads = 192;
 
 template <int BN, int KCH>
-struct ConvCfg {
-  static constexpr int kABytes = kBM * KCH * 2;
-  static constexpr int kBBytes = BN * KCH * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBudget = 200 * 1024;
-  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  // stage buffers + 1024 alignment slack + barriers/scale/shift
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 2 * 512 * 4;
+struct HaloCfg {
+  static constexpr int kRowBytes = KCH * 2;
+  static constexpr int kABytes = kBoxRows * kRowBytes;             // bytes the TMA writes
+  static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;    // ring pitch
+  static constexpr int kBBytes = BN * kRowBytes;
+  static constexpr int kNB = 8;                                    // weight ring depth
+  static constexpr int kBudget = 212 * 1024;
+  static constexpr int kNARaw = (kBudget - kNB * kBBytes) / kASlot;
+  static constexpr int kNA = kNARaw > 4 ? 4 : kNARaw;
+  static constexpr int kTmemCols = 4 * BN <= 256 ? 256 : 512;
+  static constexpr int kDataBytes = kNA * kASlot + kNB * kBBytes;
+  static constexpr int kSmemBytes = kDataBytes + 1024 + 512 + 2 * 512 * 4;
+  static_assert(kNA >= 2, "need at least two activation slots");
+  static_assert(4 * BN <= 512, "TMEM: 2 tiles x 2 stages x BN columns");
 };
 
 template <int BN, int KCH>
-__global__ void __launch_bounds__(kNumThreads, 1)
-conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const ConvParams p) {
-  using Cfg = ConvCfg<BN, KCH>;
-  constexpr int kStages = Cfg::kStages;
-  constexpr uint32_t kSwz = KCH * 2;       // swizzle span in bytes == bytes per smem row
-  constexpr uint32_t kSBO = 8 * KCH * 2;   // 8-row core-matrix group pitch
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, 0, 0);
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const HaloParams p) {
+  using Cfg = HaloCfg<BN, KCH>;
+  constexpr int kNA = Cfg::kNA, kNB = Cfg::kNB;
+  constexpr uint32_t kRB = Cfg::kRowBytes;
+  constexpr uint32_t kSwz = kRB;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  // layout: [stages x (A | B)] [barriers 256 B] [scale 512 f32] [shift 512 f32]
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
-  auto tfull_bar = [&](int s) { return bar_base + 128u + 8u * s; };
-  auto tempty_bar = [&](int s) { return bar_base + 144u + 8u * s; };
-  const uint32_t tmem_slot = bar_base + 160u;
-  float* s_scale = reinterpret_cast<float*>(smem_al + kStages * Cfg::kStageBytes + 256);
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + kNA * Cfg::kASlot;
+  const uint32_t bar_base = smem_base + Cfg::kDataBytes;
+  auto afull = [&](int s) { return bar_base + 8u * s; };            // 4
+  auto aempty = [&](int s) { return bar_base + 32u + 8u * s; };     // 4
+  auto bfull = [&](int s) { return bar_base + 64u + 8u * s; };      // 8
+  auto bempty = [&](int s) { return bar_base + 128u + 8u * s; };    // 8
+  auto tfull = [&](int s) { return bar_base + 192u + 8u * s; };     // 2
+  auto tempty = [&](int s) { return bar_base + 208u + 8u * s; };    // 2
+  const uint32_t tmem_slot = bar_base + 224u;
+  float* s_scale = reinterpret_cast<float*>(smem_al + Cfg::kDataBytes + 512);
   float* s_shift = s_scale + 512;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int TW = 1 << p.tw_log2;
-  const int num_tiles = p.num_m_tiles * p.num_n_blks;
+  const int num_items = p.num_patches * p.num_n_blks;
   const int k_chunks = p.Cin / KCH;
-  const int k_iters = 9 * k_chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
-    }
+    for (int s = 0; s < kNA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < kNB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   if (p.scale != nullptr) {
-    for (int c = threadIdx.x; c < p.Cout; c += kNumThreads) {
+    for (int c = threadIdx.x; c < p.Cout; c += kHaloThreads) {
       s_scale[c] = p.scale[c];
       s_shift[c] = p.shift[c];
     }
@@ -117,32 +129,33 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_al + kStages * Cfg::kStageBytes + 160);
+  const uint32_t tmem_base =
+      *reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::kDataBytes + 224);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile / p.num_m_tiles;
-        const int m_tile = tile - n_blk * p.num_m_tiles;
-        const int twi = m_tile % p.tiles_w;
-        const int t2 = m_tile / p.tiles_w;
-        const int thi = t2 % p.tiles_h;
-        const int img = t2 / p.tiles_h;
-        const int w0 = twi << p.tw_log2;
-        const int h0 = thi * (kBM >> p.tw_log2);
-        for (int tap = 0; tap < 9; ++tap) {
-          const int r = tap / 3, s = tap - 3 * r;
-          for (int kc = 0; kc < k_chunks; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-            const uint32_t b_dst = a_dst + Cfg::kABytes;
-            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_4d(a_dst, &tmA, full_bar(stage), kc * KCH, w0 + s - 1, h0 + r - 1, img);
-            tma_load_2d(b_dst, &tmB, full_bar(stage), tap * p.Cin + kc * KCH, n_blk * BN);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int n_blk = item / p.num_patches;
+        const int patch = item - n_blk * p.num_patches;
+        const int pw = patch % p.patches_w;
+        const int t2 = patch / p.patches_w;
+        const int ph = t2 % p.patches_h;
+        const int img = t2 / p.patches_h;
+        const int w0 = pw * kPatch, h0 = ph * kPatch;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(aempty(sa), pa ^ 1u);
+          mbar_arrive_expect_tx(afull(sa), Cfg::kABytes);
+          tma_load_4d(a_base + sa * Cfg::kASlot, &tmA, afull(sa), kc * KCH, w0 - 1, h0 - 1, img);
+          if (++sa == kNA) { sa = 0; pa ^= 1u; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bempty(sb), pb ^ 1u);
+            mbar_arrive_expect_tx(bfull(sb), Cfg::kBBytes);
+            tma_load_2d(b_base + sb * Cfg::kBBytes, &tmB, bfull(sb), tap * p.Cin + kc * KCH,
+                        n_blk * BN);
+            if (++sb == kNB) { sb = 0; pb ^= 1u; }
           }
         }
       }
@@ -150,36 +163,51 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        mbar_wait(tempty(as), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int ki = 0; ki < k_iters; ++ki) {
-          mbar_wait(full_bar(stage), phase);
+        const uint32_t d_tmem = tmem_base + as * 2 * BN;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(afull(sa), pa);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t b_addr = a_addr + Cfg::kABytes;
+          const uint32_t a_lo = smem_desc_lo(a_base + sa * Cfg::kASlot, 16);
 #pragma unroll
-          for (int k = 0; k < KCH / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, kSBO, kSwz);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, kSBO, kSwz);
-            umma_bf16(d_tmem, da, db, kIdesc, (ki | k) != 0 ? 1u : 0u);
+          for (int tap = 0; tap < 9; ++tap) {
+            constexpr uint32_t kAHi = smem_desc_hi(kBox * kRB, kSwz);
+            constexpr uint32_t kBHi = smem_desc_hi(8 * kRB, kSwz);
+            const int r = tap / 3, s = tap - 3 * r;
+            mbar_wait(bfull(sb), pb);
+            tc_fence_after();
+            const uint32_t b_lo = smem_desc_lo(b_base + sb * Cfg::kBBytes, 16);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+#pragma unroll
+              for (int k = 0; k < KCH / 16; ++k) {
+                // tap shift (r, s), tile half t and K slice k are compile-time byte offsets
+                const uint32_t a_off = (uint32_t(r * kBox + t * 8 + s) * kRB + k * 32) >> 4;
+                umma_bf16(d_tmem + t * BN, smem_desc_join(a_lo + a_off, kAHi),
+                          smem_desc_join(b_lo + ((k * 32) >> 4), kBHi), kIdesc,
+                          (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
+              }
+            }
+            umma_commit(bempty(sb));
+            if (++sb == kNB) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          umma_commit(aempty(sa));
+          if (++sa == kNA) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+        umma_commit(tfull(as));
       }
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
-    const int row = quad * 32 + lane;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // MMA tile row = (th, tw) = (row >> 3, row & 7)
     const int ew = warp - 2;
     const bool do_stats = p.stat_partials != nullptr;
     const bool do_affine = p.scale != nullptr;
@@ -200,78 +228,80 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int n_blk = tile / p.num_m_tiles;
-      const int m_tile = tile - n_blk * p.num_m_tiles;
-      const int twi = m_tile % p.tiles_w;
-      const int t2 = m_tile / p.tiles_w;
-      const int thi = t2 % p.tiles_h;
-      const int img = t2 / p.tiles_h;
-      const int pw = (twi << p.tw_log2) + (row & (TW - 1));
-      const int ph = thi * (kBM >> p.tw_log2) + (row >> p.tw_log2);
-      const bool valid = (pw < p.W) && (ph < p.H);
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int n_blk = item / p.num_patches;
+      const int patch = item - n_blk * p.num_patches;
+      const int pw = patch % p.patches_w;
+      const int t2 = patch / p.patches_w;
+      const int ph = t2 % p.patches_h;
+      const int img = t2 / p.patches_h;
       if (n_blk != cur_n_blk) { flush_stats(); cur_n_blk = n_blk; }
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(tfull_bar(as), aphase);
+      mbar_wait(tfull(as), aphase);
       tc_fence_after();
-      __nv_bfloat16* yrow = p.y + ((size_t)(img * p.H + ph) * p.W + pw) * p.ldy + n_blk * BN;
+      const int py = ph * kPatch + (row >> 3);
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * BN + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
+      for (int t = 0; t < 2; ++t) {
+        const int px = pw * kPatch + t * 8 + (row & 7);
+        const bool valid = (px < p.W) && (py < p.H);
+        __nv_bfloat16* yrow = p.y + ((size_t)(img * p.H + py) * p.W + px) * p.ldy + n_blk * BN;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (do_affine) {
-          const int cb = n_blk * BN + c * 32;
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * 2 * BN + t * BN + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = fmaf(v[j], s_scale[cb + j], s_shift[cb + j]);
-            if (p.relu) v[j] = fmaxf(v[j], 0.f);
-          }
-        }
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(yrow + c * 32);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (do_affine) {
+            const int cb = n_blk * BN + c * 32;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-            o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-            o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-            o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-            dst[q] = o;
-          }
-        }
-        if (do_stats) {
-          float q[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = valid ? v[j] : 0.f;
-            q[j] = v[j] * v[j];
-          }
-          // transpose-reduce over the 32 lanes: lane l ends with column l's total
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send = upper ? v[i] : v[i + off];
-              const float keep = upper ? v[i + off] : v[i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-              const float send2 = upper ? q[i] : q[i + off];
-              const float keep2 = upper ? q[i + off] : q[i];
-              q[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            for (int j = 0; j < 32; ++j) {
+              v[j] = fmaf(v[j], s_scale[cb + j], s_shift[cb + j]);
+              if (p.relu) v[j] = fmaxf(v[j], 0.f);
             }
           }
-          acc_sum[c] += v[0];
-          acc_sq[c] += q[0];
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(yrow + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              dst[q] = o;
+            }
+          }
+          if (do_stats) {
+            float q[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = valid ? v[j] : 0.f;
+              q[j] = v[j] * v[j];
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send = upper ? v[i] : v[i + off];
+                const float keep = upper ? v[i + off] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                const float send2 = upper ? q[i] : q[i + off];
+                const float keep2 = upper ? q[i + off] : q[i];
+                q[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+              }
+            }
+            acc_sum[c] += v[0];
+            acc_sq[c] += q[0];
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) mbar_arrive(tempty(as));
     }
     flush_stats();
   }
@@ -286,27 +316,30 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <int BN, int KCH>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p,
                        cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, KCH>;
-  auto kern = conv3x3_igemm_kernel<BN, KCH>;
+  using Cfg = HaloCfg<BN, KCH>;
+  auto kern = conv3x3_halo_kernel<BN, KCH>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
         cudaSuccess)
-      return check_launch("conv3x3 smem attribute");
+      return check_launch("conv3x3_halo smem attribute");
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_blks;
+  const int items = p.num_patches * p.num_n_blks;
   int grid = sm_count();
-  if (grid > tiles) grid = tiles;
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
-  return check_launch("conv3x3_igemm");
+  if (grid > items) grid = items;
+  kern<<<grid, kHaloThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  return check_launch("conv3x3_halo");
 }
 
 static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, long ldy, int N,
                             int H, int W, int Cin, int Cout, const float* scale, const float* shift,
                             int relu, float* stat_partials, cudaStream_t stream) {
+  if (g_conv_impl == 1)
+    return v1::conv3x3_dispatch(x, ldx, w_packed, y, ldy, N, H, W, Cin, Cout, scale, shift, relu,
+                                stat_partials, stream);
   if (N <= 0 || H <= 0 || W <= 0) return FPB200_ERR_SHAPE;
   if (Cin % 16 != 0 || Cout % 64 != 0 || Cout > 2048) return FPB200_ERR_SHAPE;
   if ((ldx % 8) != 0 || (ldy % 8) != 0 || ldx < Cin || ldy < Cout) return FPB200_ERR_SHAPE;
@@ -315,23 +348,13 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
     return FPB200_ERR_ALIGN;
   if (scale != nullptr && Cout > 512) return FPB200_ERR_SHAPE;
   const int KCH = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
-  const int BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
 
-  // tile geometry: choose TW minimising padded area (ties -> wider rows)
-  int best_l = 3;
-  long best_area = -1;
-  for (int l = 3; l <= 7; ++l) {
-    const int tw = 1 << l, th = kBM >> l;
-    const long area = (long)((W + tw - 1) / tw) * tw * (long)((H + th - 1) / th) * th;
-    if (best_area < 0 || area <= best_area) { best_area = area; best_l = l; }
-  }
-  ConvParams p;
+  HaloParams p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.tw_log2 = best_l;
-  const int TW = 1 << best_l, TH = kBM >> best_l;
-  p.tiles_w = (W + TW - 1) / TW;
-  p.tiles_h = (H + TH - 1) / TH;
-  p.num_m_tiles = N * p.tiles_h * p.tiles_w;
+  p.patches_w = (W + kPatch - 1) / kPatch;
+  p.patches_h = (H + kPatch - 1) / kPatch;
+  p.num_patches = N * p.patches_h * p.patches_w;
   p.num_n_blks = Cout / BN;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.ldy = ldy;
@@ -339,7 +362,7 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
   p.stat_partials = stat_partials;
 
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_act(&tmA, x, N, H, W, Cin, ldx, KCH, TW, TH);
+  int rc = make_tmap_act(&tmA, x, N, H, W, Cin, ldx, KCH, kBox, kBox);
   if (rc != FPB200_OK) return rc;
   rc = make_tmap_mat(&tmB, w_packed, Cout, 9L * Cin, KCH, BN);
   if (rc != FPB200_OK) return rc;
@@ -348,24 +371,27 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
                         stream) != cudaSuccess)
       return check_launch("conv3x3 stat memset");
   }
-#define FP_CONV_CASE(bn, kch) \
-  if (BN == bn && KCH == kch) return launch_conv<bn, kch>(tmA, tmB, p, stream);
-  FP_CONV_CASE(256, 64)
-  FP_CONV_CASE(128, 64)
-  FP_CONV_CASE(64, 64)
-  FP_CONV_CASE(256, 32)
-  FP_CONV_CASE(128, 32)
-  FP_CONV_CASE(64, 32)
-  FP_CONV_CASE(256, 16)
-  FP_CONV_CASE(128, 16)
-  FP_CONV_CASE(64, 16)
-#undef FP_CONV_CASE
+#define FP_HALO_CASE(bn, kch) \
+  if (BN == bn && KCH == kch) return launch_halo<bn, kch>(tmA, tmB, p, stream);
+  FP_HALO_CASE(128, 64)
+  FP_HALO_CASE(64, 64)
+  FP_HALO_CASE(128, 32)
+  FP_HALO_CASE(64, 32)
+  FP_HALO_CASE(128, 16)
+  FP_HALO_CASE(64, 16)
+#undef FP_HALO_CASE
   return FPB200_ERR_SHAPE;
 }
 
 }  // namespace fp
 
 extern "C" {
+
+// bring-up hook (not part of the public header): choose the conv implementation under test
+int fpb200_debug_conv_mode(int impl) {
+  fp::g_conv_impl = impl;
+  return 0;
+}
 
 int fpb200_conv_stat_rows(void) { return 4 * fp::sm_count(); }
 

@@ -152,17 +152,22 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         tc_fence_after();
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
         const uint32_t sb = sa + Cfg::kNA * kASlotBytes;
+        constexpr uint32_t kAHi = smem_desc_hi(1024, 128);
+        constexpr uint32_t kBHi = smem_desc_hi(kBSBO, kBSwz);
+        const uint32_t a_lo = smem_desc_lo(sa, kASlotBytes);
+        const uint32_t b_lo = smem_desc_lo(sb, Cfg::kBSlotBytes);
+        const uint32_t acc = (t > t_begin) ? 1u : 0u;
 #pragma unroll
         for (int g = 0; g < Cfg::kGroups; ++g) {
-          const uint32_t a_addr = MODE == 0 ? sa : sa + 2 * g * kASlotBytes;
-          const uint32_t b_addr = MODE == 0 ? sb + g * NB * Cfg::kBSlotBytes : sb;
+          // compile-time operand offsets (bytes): slot of the group, then 16 pixels per K step
+          constexpr uint32_t kAStep = 2048, kBStep = 2 * kBSBO;
+          const uint32_t a_g = MODE == 0 ? 0u : uint32_t(2 * g) * kASlotBytes;
+          const uint32_t b_g = MODE == 0 ? uint32_t(g * NB) * Cfg::kBSlotBytes : 0u;
 #pragma unroll
           for (int k = 0; k < kWgBK / 16; ++k) {
-            // 16 pixels = two 8-row groups; rows are 128 B (A) / NBW*2 B (B)
-            const uint64_t da = make_smem_desc(a_addr + k * 2048, kASlotBytes, 1024, 128);
-            const uint64_t db =
-                make_smem_desc(b_addr + k * 2 * kBSBO, Cfg::kBSlotBytes, kBSBO, kBSwz);
-            umma_bf16(tmem_base + g * Cfg::kN, da, db, kIdesc, (t > t_begin || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base + g * Cfg::kN, smem_desc_join(a_lo + ((a_g + k * kAStep) >> 4), kAHi),
+                      smem_desc_join(b_lo + ((b_g + k * kBStep) >> 4), kBHi), kIdesc,
+                      k == 0 ? acc : 1u);
           }
         }
         umma_commit(empty_bar(stage));

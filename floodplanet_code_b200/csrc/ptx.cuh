@@ -198,6 +198,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// Split form for the MMA issue loop: the issuing thread is a single lane running a dependent
+// instruction chain, so rebuilding a 64-bit descriptor per MMA (~30 ALU ops) costs more than
+// the MMA itself takes on the tensor pipe.  The high word is a per-operand constant and the
+// low word is (address >> 4) plus constant offsets, so advancing an operand is one IADD.
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t swizzle_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) |
+         ((swizzle_bytes == 128 ? 2u : (swizzle_bytes == 64 ? 4u : 6u)) << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo, uint32_t hi) {
+  return (uint64_t(hi) << 32) | uint64_t(lo);
+}
+
 // ---------------------------------------------------------------------------
 // bf16 packing
 // ---------------------------------------------------------------------------

@@ -21,6 +21,17 @@ def ops():
     return _ops
 
 
+@pytest.fixture(params=["halo", "per_tap"])
+def conv_impl(request):
+    """Both conv generations stay under test: the halo kernel (product path) and the
+    first-generation one-box-per-tap kernel it was validated against."""
+    from floodplanet_code_b200 import capi
+    lib = capi.load()
+    lib.fpb200_debug_conv_mode({"halo": 2, "per_tap": 1}[request.param])
+    yield request.param
+    lib.fpb200_debug_conv_mode(2)
+
+
 def rel(a, b):
     a = a.double().flatten()
     b = b.double().flatten()
@@ -61,7 +72,7 @@ CONV_SHAPES = [
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES)
-def test_conv3x3_fprop_and_stats(ops, n, h, w, cin, cout):
+def test_conv3x3_fprop_and_stats(ops, conv_impl, n, h, w, cin, cout):
     x = rand_act(n, h, w, cin, 1)
     wt = rand_w(cout, cin, 2)
     wp = ops.repack_fprop(wt, cin)
@@ -80,7 +91,7 @@ def test_conv3x3_fprop_and_stats(ops, n, h, w, cin, cout):
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (1, 20, 24, 128, 256)])
-def test_conv3x3_fprop_affine_relu_into_concat_view(ops, n, h, w, cin, cout):
+def test_conv3x3_fprop_affine_relu_into_concat_view(ops, conv_impl, n, h, w, cin, cout):
     x = rand_act(n, h, w, cin, 3)
     wt = rand_w(cout, cin, 4)
     wp = ops.repack_fprop(wt, cin)
@@ -97,7 +108,7 @@ def test_conv3x3_fprop_affine_relu_into_concat_view(ops, n, h, w, cin, cout):
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (1, 20, 24, 128, 256), (1, 19, 19, 256, 64),
                                             (1, 16, 16, 1024, 512)])
-def test_conv3x3_dgrad(ops, n, h, w, cin, cout):
+def test_conv3x3_dgrad(ops, conv_impl, n, h, w, cin, cout):
     dy = rand_act(n, h, w, cout, 6)
     wt = rand_w(cout, cin, 7)
     wd = ops.repack_dgrad(wt)

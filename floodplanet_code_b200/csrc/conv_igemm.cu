@@ -29,9 +29,12 @@
 //
 // Fused epilogues (runtime flags, warp-uniform):
 //   * per-channel affine (+ReLU): eval-mode BatchNorm folded to scale/shift
-//   * BatchNorm batch-statistic partials: per-channel sum / sum of squares of the fp32
-//     accumulators (shuffle transpose-reduce per warp, accumulated across the CTA's patches)
-//   * bf16 cast + 16-byte stores into an NHWC view with arbitrary pixel pitch.
+//   * bf16 cast, staged per warp in swizzled smem and written with TMA stores (8 px x 4 rows
+//     x 64 ch boxes; ragged image edges are clipped by the TMA unit) into an NHWC view with
+//     arbitrary pixel pitch
+//   * BatchNorm batch-statistic partials: per-channel sum / sum of squares of the stored bf16
+//     values, read back conflict-free from the staging tile, accumulated in registers across
+//     all patches of the persistent CTA.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -69,12 +72,14 @@ struct HaloCfg {
   static constexpr int kABytes = kBoxRows * kRowBytes;             // bytes the TMA writes
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;    // ring pitch
   static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kNB = 8;                                    // weight ring depth
+  static constexpr int kNB = BN >= 128 ? 7 : 8;                    // weight ring depth
+  static constexpr int kStageOut = 4 * 4096;                       // epilogue staging, 4 KB per warp
   static constexpr int kBudget = 212 * 1024;
-  static constexpr int kNARaw = (kBudget - kNB * kBBytes) / kASlot;
+  static constexpr int kNARaw = (kBudget - kStageOut - kNB * kBBytes) / kASlot;
   static constexpr int kNA = kNARaw > 4 ? 4 : kNARaw;
   static constexpr int kTmemCols = 4 * BN <= 256 ? 256 : 512;
-  static constexpr int kDataBytes = kNA * kASlot + kNB * kBBytes;
+  static constexpr int kRingBytes = kNA * kASlot + ((kNB * kBBytes + 1023) / 1024 * 1024);
+  static constexpr int kDataBytes = kRingBytes + kStageOut;
   static constexpr int kSmemBytes = kDataBytes + 1024 + 512 + 2 * 512 * 4;
   static_assert(kNA >= 2, "need at least two activation slots");
   static_assert(4 * BN <= 512, "TMEM: 2 tiles x 2 stages x BN columns");
@@ -83,7 +88,7 @@ struct HaloCfg {
 template <int BN, int KCH>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const HaloParams p) {
+                    const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
   using Cfg = HaloCfg<BN, KCH>;
   constexpr int kNA = Cfg::kNA, kNB = Cfg::kNB;
   constexpr uint32_t kRB = Cfg::kRowBytes;
@@ -95,6 +100,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + kNA * Cfg::kASlot;
+  const uint32_t stg_base = smem_base + Cfg::kRingBytes;
   const uint32_t bar_base = smem_base + Cfg::kDataBytes;
   auto afull = [&](int s) { return bar_base + 8u * s; };            // 4
   auto aempty = [&](int s) { return bar_base + 32u + 8u * s; };     // 4
@@ -114,6 +120,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
     for (int s = 0; s < kNA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < kNB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
@@ -206,24 +213,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
+    // Per (MMA tile, 64-channel unit): TMEM -> registers -> (affine/ReLU) -> bf16 -> this warp's
+    // 32-row x 128-byte staging tile in smem (128B-swizzled) -> one TMA store of the
+    // 8 px x 4 rows x 64 ch box.  BatchNorm statistics are column sums over the staged tile
+    // (i.e. of exactly the bf16 values that are stored and later normalised).
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // MMA tile row = (th, tw) = (row >> 3, row & 7)
     const int ew = warp - 2;
     const bool do_stats = p.stat_partials != nullptr;
     const bool do_affine = p.scale != nullptr;
-    float acc_sum[BN / 32], acc_sq[BN / 32];
+    const uint32_t stg = stg_base + ew * 4096;
+    const uint32_t stg_row = stg + lane * 128;
+    constexpr int kUnits = BN / 64;
+    float acc_sum[kUnits][2], acc_sq[kUnits][2];
 #pragma unroll
-    for (int c = 0; c < BN / 32; ++c) { acc_sum[c] = 0.f; acc_sq[c] = 0.f; }
+    for (int u = 0; u < kUnits; ++u) { acc_sum[u][0] = acc_sum[u][1] = acc_sq[u][0] = acc_sq[u][1] = 0.f; }
     int cur_n_blk = -1;
     auto flush_stats = [&]() {
       if (do_stats && cur_n_blk >= 0) {
         float* dst = p.stat_partials + (size_t)(blockIdx.x * 4 + ew) * 2 * p.Cout + cur_n_blk * BN;
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          dst[c * 32 + lane] = acc_sum[c];
-          dst[p.Cout + c * 32 + lane] = acc_sq[c];
-          acc_sum[c] = 0.f;
-          acc_sq[c] = 0.f;
+        for (int u = 0; u < kUnits; ++u) {
+          *reinterpret_cast<float2*>(dst + u * 64 + 2 * lane) = make_float2(acc_sum[u][0], acc_sum[u][1]);
+          *reinterpret_cast<float2*>(dst + p.Cout + u * 64 + 2 * lane) = make_float2(acc_sq[u][0], acc_sq[u][1]);
+          acc_sum[u][0] = acc_sum[u][1] = acc_sq[u][0] = acc_sq[u][1] = 0.f;
         }
       }
     };
@@ -245,25 +258,29 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int t = 0; t < 2; ++t) {
         const int px = pw * kPatch + t * 8 + (row & 7);
         const bool valid = (px < p.W) && (py < p.H);
-        __nv_bfloat16* yrow = p.y + ((size_t)(img * p.H + py) * p.W + px) * p.ldy + n_blk * BN;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * 2 * BN + t * BN + c * 32, r);
-          tmem_ld_wait();
-          float v[32];
+        for (int u = 0; u < kUnits; ++u) {
+          // the previous TMA store must have finished reading the staging tile
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (do_affine) {
-            const int cb = n_blk * BN + c * 32;
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * 2 * BN + t * BN + u * 64 +
+                              hlf * 32, r);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = fmaf(v[j], s_scale[cb + j], s_shift[cb + j]);
-              if (p.relu) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (do_affine) {
+              const int cb = n_blk * BN + u * 64 + hlf * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                v[j] = fmaf(v[j], s_scale[cb + j], s_shift[cb + j]);
+                if (p.relu) v[j] = fmaxf(v[j], 0.f);
+              }
             }
-          }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(yrow + c * 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 o;
@@ -271,31 +288,31 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
               o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
               o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              dst[q] = o;
+              st_shared_v4(stg_row + (uint32_t((hlf * 4 + q) ^ (lane & 7)) << 4), o);
             }
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmY, stg, n_blk * BN + u * 64, pw * kPatch + t * 8,
+                         ph * kPatch + quad * 4, img);
+            tma_store_commit();
+          }
           if (do_stats) {
-            float q[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = valid ? v[j] : 0.f;
-              q[j] = v[j] * v[j];
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-              const bool upper = (lane & off) != 0;
-#pragma unroll
-              for (int i = 0; i < off; ++i) {
-                const float send = upper ? v[i] : v[i + off];
-                const float keep = upper ? v[i + off] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                const float send2 = upper ? q[i] : q[i + off];
-                const float keep2 = upper ? q[i + off] : q[i];
-                q[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            // lane l owns channels 2l, 2l+1 of this unit: walk the 32 staged rows
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              if ((vmask >> rr) & 1u) {
+                const uint32_t wv = ld_shared_u32(stg + rr * 128 +
+                                                  (uint32_t((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
+                const float lo = bf16_lo(wv), hi = bf16_hi(wv);
+                s0 += lo; s1 += hi;
+                q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
               }
             }
-            acc_sum[c] += v[0];
-            acc_sq[c] += q[0];
+            acc_sum[u][0] += s0; acc_sum[u][1] += s1;
+            acc_sq[u][0] += q0; acc_sq[u][1] += q1;
           }
         }
       }
@@ -304,6 +321,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(tempty(as));
     }
     flush_stats();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -316,8 +334,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int BN, int KCH>
-static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p,
-                       cudaStream_t stream) {
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                       const HaloParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, KCH>;
   auto kern = conv3x3_halo_kernel<BN, KCH>;
   static bool attr_set = false;
@@ -330,7 +348,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
   const int items = p.num_patches * p.num_n_blks;
   int grid = sm_count();
   if (grid > items) grid = items;
-  kern<<<grid, kHaloThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  kern<<<grid, kHaloThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
   return check_launch("conv3x3_halo");
 }
 
@@ -361,10 +379,12 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.stat_partials = stat_partials;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmY;
   int rc = make_tmap_act(&tmA, x, N, H, W, Cin, ldx, KCH, kBox, kBox);
   if (rc != FPB200_OK) return rc;
   rc = make_tmap_mat(&tmB, w_packed, Cout, 9L * Cin, KCH, BN);
+  if (rc != FPB200_OK) return rc;
+  rc = make_tmap_act(&tmY, y, N, H, W, Cout, ldy, 64, 8, 4);  // epilogue store box: 8 px x 4 rows x 64 ch
   if (rc != FPB200_OK) return rc;
   if (stat_partials != nullptr) {
     if (cudaMemsetAsync(stat_partials, 0, (size_t)fpb200_conv_stat_rows() * 2 * Cout * sizeof(float),
@@ -372,7 +392,7 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
       return check_launch("conv3x3 stat memset");
   }
 #define FP_HALO_CASE(bn, kch) \
-  if (BN == bn && KCH == kch) return launch_halo<bn, kch>(tmA, tmB, p, stream);
+  if (BN == bn && KCH == kch) return launch_halo<bn, kch>(tmA, tmB, tmY, p, stream);
   FP_HALO_CASE(128, 64)
   FP_HALO_CASE(64, 64)
   FP_HALO_CASE(128, 32)

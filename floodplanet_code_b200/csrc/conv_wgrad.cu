@@ -5,34 +5,40 @@
 //
 // is a GEMM whose reduction dimension is the PIXEL axis (up to 16.8 M long) and whose
 // output is tiny, so it is split-K: every CTA owns one output tile and one contiguous range
-// of 64-pixel tiles, accumulates in TMEM, and writes fp32 partials that a second kernel
-// sums deterministically into the OIHW fp32 gradient.
+// of 64-pixel tiles (4 image rows x 16 pixels), accumulates in TMEM, and writes fp32
+// partials that a second kernel sums deterministically into the OIHW fp32 gradient.
 //
 // Both GEMM operands are "MN-major": in NHWC memory the channel axis (the GEMM M resp. N
-// axis) is the contiguous one and the pixel axis (GEMM K) is strided.  TMA drops a
-// [64 pixels][64 channels] box into 128B-swizzled smem (one 128-byte row per pixel) and
-// tcgen05.mma consumes it directly with the transposed-operand bits of the instruction
-// descriptor set -- no transposes anywhere.  The 3x3 taps are nine shifted views of the same
-// tensor; the shift is only a TMA coordinate offset and the conv halo is the TMA
-// out-of-bounds zero fill.
+// axis) is the contiguous one and the pixel axis (GEMM K) is strided.  TMA drops pixel boxes
+// into 128B-swizzled smem (one 128-byte row per pixel, 64 channels) and tcgen05.mma consumes
+// them directly with the transposed-operand bits of the instruction descriptor set -- no
+// transposes anywhere.  One K step of an MMA is one image row of the tile (16 pixels = two
+// 8-row swizzle groups).
+//
+// The 3x3 taps are shifted views of ONE box that carries the halo (zero filled by TMA outside
+// the image): a tap is only a different descriptor start address, exactly as in the fprop
+// kernel, so each operand byte enters shared memory once per tile instead of once per tap.
 //
 // Two operand arrangements keep UMMA_M = 128 for every layer of the UNet:
-//   MODE_X_SHIFT  (Cout >= 128): A = 128 output channels of dy (unshifted),
-//                  B = three column-shifted x boxes of one filter row, N = 64 or 128 each.
-//   MODE_DY_SHIFT (Cout == 64 per block): A = TWO differently shifted dy boxes stacked on M
-//                  (2 taps x 64 channels), B = unshifted x; 5 such pairs cover the 9 taps.
+//   MODE_X_SHIFT  (Cout % 128 == 0): A = 128 output channels of dy (no halo); B = one filter
+//                  row of x, box 18 px wide, the three taps s = start address + s pixels.
+//                  Work item = (128 co, 64*NB ci, filter row r): 3 accumulators of 64*NB cols.
+//   MODE_DY_SHIFT (Cout == 64 blocks): the SHIFT moves to dy (dW[tap] = sum_q dy[q-tap] x[q]):
+//                  A = dy box with halo (18 x 6 px); two taps are stacked on M (2 x 64 co) by
+//                  pointing the descriptor's second 64-row block (LBO) at the other tap's
+//                  offset inside the same box; B = x, unshifted.  5 pairs cover the 9 taps.
 #include "host_common.h"
 #include "ptx.cuh"
 
 namespace fp {
 
 constexpr int kWgThreads = 192;
-constexpr int kWgBK = 64;             // pixels per pipeline stage
-constexpr int kASlotBytes = kWgBK * 128;  // [64 px][64 ch] bf16
+constexpr int kWgTW = 16, kWgTH = 4;        // pixel tile: 4 image rows x 16 pixels
+constexpr int kWgBK = kWgTW * kWgTH;        // 64 pixels per pipeline stage
+constexpr int kWgBoxW = kWgTW + 2;
 
 struct WgradParams {
   int N, H, W;
-  int tw_log2;           // pixel tile = (64 >> tw_log2) rows x (1 << tw_log2) cols
   int tiles_w, tiles_h;  // per image
   int num_pix_tiles;
   int ksplit;
@@ -45,16 +51,29 @@ struct WgradParams {
 
 template <int MODE, int NBW, int NB>
 struct WgCfg {
-  static constexpr int kNA = MODE == 0 ? 2 : 10;          // A slots (64-channel dy boxes)
-  static constexpr int kNBS = MODE == 0 ? 3 * NB : 1;     // B slots
-  static constexpr int kBSlotBytes = kWgBK * NBW * 2;
-  static constexpr int kStageBytes = kNA * kASlotBytes + kNBS * kBSlotBytes;
+  // A = dy.  mode 0: two [64 px][64 co] blocks; mode 1: one haloed box 18 x 6 px (padded slot)
+  static constexpr int kABlock = MODE == 0 ? kWgBK * 128 : kWgBoxW * (kWgTH + 2) * 128;
+  static constexpr int kABytes = MODE == 0 ? 2 * kABlock : kABlock;          // TMA bytes
+  static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024 + (MODE == 0 ? 0 : 1024);
+  // B = x.  mode 0: NB blocks of one filter row with halo [18 x 4 px][64 ci]; mode 1: [64 px][NBW]
+  static constexpr int kBBlock = MODE == 0 ? kWgBoxW * kWgTH * 128 : kWgBK * NBW * 2;
+  static constexpr int kBBytes = MODE == 0 ? NB * kBBlock : kBBlock;
+  static constexpr int kBSlot = (kBBytes + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kASlot + kBSlot;
+  static constexpr int kTxBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kGroups = MODE == 0 ? 3 : 5;
   static constexpr int kN = NBW * NB;                     // UMMA N per group
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
+
+// MODE_DY_SHIFT tap pairing.  Box row offset of tap (r,s) is (2-r)*18 + (2-s); group g stacks
+// tap 8-2g (M rows 0..63) and tap 7-2g (M rows 64..127); group 4 is tap 0 plus a discarded half.
+__host__ __device__ constexpr int wg_pair_offset(int g) {
+  return g == 0 ? 0 : (g == 1 ? 2 : (g == 2 ? kWgBoxW + 1 : (g == 3 ? 2 * kWgBoxW : 2 * kWgBoxW + 2)));
+}
+__host__ __device__ constexpr int wg_pair_lbo_rows(int g) { return g == 1 ? kWgBoxW - 2 : 1; }
 
 template <int MODE, int NBW, int NB>
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -63,8 +82,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   using Cfg = WgCfg<MODE, NBW, NB>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kIdesc = make_idesc_bf16(128, Cfg::kN, 1, 1);
-  constexpr uint32_t kBSwz = NBW * 2;
-  constexpr uint32_t kBSBO = 8 * NBW * 2;
+  constexpr uint32_t kBRow = MODE == 0 ? 128 : NBW * 2;   // bytes per pixel row of B
+  constexpr uint32_t kBSwz = kBRow;
+  constexpr uint32_t kBSBO = 8 * kBRow;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -115,29 +135,21 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         const int t2 = t / p.tiles_w;
         const int thi = t2 % p.tiles_h;
         const int img = t2 / p.tiles_h;
-        const int w0 = twi << p.tw_log2;
-        const int h0 = thi * (kWgBK >> p.tw_log2);
+        const int w0 = twi * kWgTW;
+        const int h0 = thi * kWgTH;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-        const uint32_t sb = sa + Cfg::kNA * kASlotBytes;
-        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kASlot;
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kTxBytes);
         if (MODE == 0) {
           tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0, h0, img);
-          tma_load_4d(sa + kASlotBytes, &tmDY, full_bar(stage), co0 + 64, w0, h0, img);
+          tma_load_4d(sa + Cfg::kABlock, &tmDY, full_bar(stage), co0 + 64, w0, h0, img);
 #pragma unroll
-          for (int s = 0; s < 3; ++s)
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-              tma_load_4d(sb + (s * NB + b) * Cfg::kBSlotBytes, &tmX, full_bar(stage),
-                          ci0 + b * 64, w0 + s - 1, h0 + r_idx - 1, img);
+          for (int b = 0; b < NB; ++b)
+            tma_load_4d(sb + b * Cfg::kBBlock, &tmX, full_bar(stage), ci0 + b * 64, w0 - 1,
+                        h0 + r_idx - 1, img);
         } else {
-#pragma unroll
-          for (int a = 0; a < 10; ++a) {
-            const int tap = a < 9 ? a : 8;
-            const int r = tap / 3, s = tap - 3 * r;
-            tma_load_4d(sa + a * kASlotBytes, &tmDY, full_bar(stage), co0, w0 - (s - 1),
-                        h0 - (r - 1), img);
-          }
+          tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0 - 1, h0 - 1, img);
           tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0, h0, img);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -151,23 +163,31 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-        const uint32_t sb = sa + Cfg::kNA * kASlotBytes;
+        const uint32_t sb = sa + Cfg::kASlot;
         constexpr uint32_t kAHi = smem_desc_hi(1024, 128);
         constexpr uint32_t kBHi = smem_desc_hi(kBSBO, kBSwz);
-        const uint32_t a_lo = smem_desc_lo(sa, kASlotBytes);
-        const uint32_t b_lo = smem_desc_lo(sb, Cfg::kBSlotBytes);
+        const uint32_t a_addr16 = (sa >> 4) & 0x3FFF;
+        const uint32_t b_addr16 = (sb >> 4) & 0x3FFF;
         const uint32_t acc = (t > t_begin) ? 1u : 0u;
 #pragma unroll
         for (int g = 0; g < Cfg::kGroups; ++g) {
-          // compile-time operand offsets (bytes): slot of the group, then 16 pixels per K step
-          constexpr uint32_t kAStep = 2048, kBStep = 2 * kBSBO;
-          const uint32_t a_g = MODE == 0 ? 0u : uint32_t(2 * g) * kASlotBytes;
-          const uint32_t b_g = MODE == 0 ? uint32_t(g * NB) * Cfg::kBSlotBytes : 0u;
 #pragma unroll
-          for (int k = 0; k < kWgBK / 16; ++k) {
-            umma_bf16(tmem_base + g * Cfg::kN, smem_desc_join(a_lo + ((a_g + k * kAStep) >> 4), kAHi),
-                      smem_desc_join(b_lo + ((b_g + k * kBStep) >> 4), kBHi), kIdesc,
-                      k == 0 ? acc : 1u);
+          for (int k = 0; k < kWgTH; ++k) {   // K step k = image row k of the tile (16 pixels)
+            uint32_t a_lo, b_lo;
+            if (MODE == 0) {
+              // A: dy rows k*16.. of both 64-co blocks (LBO = block pitch)
+              a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
+              // B: x row k of the haloed filter-row box, shifted by tap s = g pixels
+              b_lo = (b_addr16 + (((k * kWgBoxW + g) * 128) >> 4)) |
+                     ((uint32_t(Cfg::kBBlock) >> 4) << 16);
+            } else {
+              // A: haloed dy box; first M block at the pair's first tap, second block LBO further
+              a_lo = (a_addr16 + (((k * kWgBoxW + wg_pair_offset(g)) * 128) >> 4)) |
+                     ((uint32_t(wg_pair_lbo_rows(g) * 128) >> 4) << 16);
+              b_lo = (b_addr16 + ((k * kWgTW * kBRow) >> 4)) | (1u << 16);
+            }
+            umma_bf16(tmem_base + g * Cfg::kN, smem_desc_join(a_lo, kAHi),
+                      smem_desc_join(b_lo, kBHi), kIdesc, k == 0 ? acc : 1u);
           }
         }
         umma_commit(empty_bar(stage));
@@ -190,15 +210,15 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         tap = r_idx * 3 + g;
       } else {
         co = co0 + (row & 63);
-        tap = 2 * g + (row >> 6);
+        tap = (row < 64) ? 8 - 2 * g : 7 - 2 * g;   // group 4: tap 0 and a discarded half (-1)
       }
-      float* dst = ws + ((size_t)co * 9 + tap) * p.Cin + ci0;
+      float* dst = ws + ((size_t)co * 9 + (tap < 0 ? 0 : tap)) * p.Cin + ci0;
 #pragma unroll
       for (int c = 0; c < Cfg::kN / 16; ++c) {
         uint32_t r[16];
         tmem_ld_32x16(tmem_base + (uint32_t(quad * 32) << 16) + g * Cfg::kN + c * 16, r);
         tmem_ld_wait();
-        if (tap < 9) {
+        if (tap >= 0) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float4 o;
@@ -241,7 +261,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 struct WgPlan {
   int mode, nbw, nb;
   int n_items, items_ci, items_r, ksplit;
-  int tw_log2, tiles_w, tiles_h, num_pix_tiles;
+  int tiles_w, tiles_h, num_pix_tiles;
 };
 
 static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl) {
@@ -258,18 +278,8 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl) {
     pl->items_ci = Cin / pl->nbw;
     pl->n_items = (Cout / 64) * pl->items_ci;
   }
-  // pixel tiles of 64: pick the shape with least padding (ties -> wider)
-  int best_l = 3;
-  long best_area = -1;
-  for (int l = 3; l <= 6; ++l) {
-    const int tw = 1 << l, th = kWgBK >> l;
-    const long area = (long)((W + tw - 1) / tw) * tw * (long)((H + th - 1) / th) * th;
-    if (best_area < 0 || area <= best_area) { best_area = area; best_l = l; }
-  }
-  pl->tw_log2 = best_l;
-  const int TW = 1 << best_l, TH = kWgBK >> best_l;
-  pl->tiles_w = (W + TW - 1) / TW;
-  pl->tiles_h = (H + TH - 1) / TH;
+  pl->tiles_w = (W + kWgTW - 1) / kWgTW;
+  pl->tiles_h = (H + kWgTH - 1) / kWgTH;
   pl->num_pix_tiles = N * pl->tiles_h * pl->tiles_w;
   // split-K so that ~2 waves of CTAs exist, but never more splits than pixel tiles
   int ks = (2 * sm_count() + pl->n_items - 1) / pl->n_items;
@@ -320,15 +330,20 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15) ||
       (reinterpret_cast<uintptr_t>(workspace) & 15))
     return FPB200_ERR_ALIGN;
-  const int TW = 1 << pl.tw_log2, TH = kWgBK >> pl.tw_log2;
   CUtensorMap tmDY, tmX;
-  rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, TW, TH);
-  if (rc != FPB200_OK) return rc;
-  rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, pl.nbw, TW, TH);
+  if (pl.mode == 0) {
+    rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgTW, kWgTH);
+    if (rc != FPB200_OK) return rc;
+    rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, 64, kWgBoxW, kWgTH);
+  } else {
+    rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgBoxW, kWgTH + 2);
+    if (rc != FPB200_OK) return rc;
+    rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, pl.nbw, kWgTW, kWgTH);
+  }
   if (rc != FPB200_OK) return rc;
   WgradParams p;
   p.N = N; p.H = H; p.W = W;
-  p.tw_log2 = pl.tw_log2; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.num_pix_tiles = pl.num_pix_tiles;
   p.ksplit = pl.ksplit; p.n_items = pl.n_items; p.items_ci = pl.items_ci; p.items_r = pl.items_r;
   p.Cout = Cout; p.Cin = Cin;

@@ -452,31 +452,38 @@ __device__ __forceinline__ void bilinear_src(int dst, float ratio, int in_size, 
   l0 = 1.f - l1;
 }
 
-__global__ void upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
-                                          __nv_bfloat16* __restrict__ out, long ldo, int N, int h,
-                                          int w, int Ho, int Wo, int CG, int pad_top,
-                                          int pad_left, float rh, float rw) {
-  const long total = (long)N * Ho * Wo * CG;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const int cg = i % CG;
-    long t = i / CG;
-    const int wo = t % Wo; t /= Wo;
-    const int ho = t % Ho;
-    const int n = t / Ho;
-    const int uh = ho - pad_top, uw = wo - pad_left;
+// One block per output row (n, ho): the vertical taps / weights are block-uniform, indices are
+// 32-bit, and consecutive threads write consecutive 16-byte channel groups of the row.
+__global__ void __launch_bounds__(256)
+upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
+                          __nv_bfloat16* __restrict__ out, long ldo, int h, int w, int Ho, int Wo,
+                          int CG, int pad_top, int pad_left, float rh, float rw) {
+  const int row = blockIdx.x;
+  const int n = row / Ho;
+  const int ho = row - n * Ho;
+  const int uh = ho - pad_top;
+  const bool row_in = uh >= 0 && uh < 2 * h;
+  int h0 = 0, h1 = 0;
+  float lh0 = 0.f, lh1 = 0.f;
+  if (row_in) bilinear_src(uh, rh, h, h0, h1, lh0, lh1);
+  const __nv_bfloat16* r0 = x + ((long)n * h + h0) * w * ldx;
+  const __nv_bfloat16* r1 = x + ((long)n * h + h1) * w * ldx;
+  __nv_bfloat16* orow = out + (long)row * Wo * ldo;
+  const int work = Wo * CG;
+  for (int i = threadIdx.x; i < work; i += blockDim.x) {
+    const int wo = i / CG;
+    const int cg = i - wo * CG;
+    const int uw = wo - pad_left;
     float o[8];
-    if (uh >= 0 && uh < 2 * h && uw >= 0 && uw < 2 * w) {
-      int h0, h1, w0, w1;
-      float lh0, lh1, lw0, lw1;
-      bilinear_src(uh, rh, h, h0, h1, lh0, lh1);
+    if (row_in && uw >= 0 && uw < 2 * w) {
+      int w0, w1;
+      float lw0, lw1;
       bilinear_src(uw, rw, w, w0, w1, lw0, lw1);
-      const __nv_bfloat16* base = x + (long)n * h * w * ldx + cg * 8;
       float v00[8], v01[8], v10[8], v11[8];
-      unpack8(*reinterpret_cast<const uint4*>(base + ((long)h0 * w + w0) * ldx), v00);
-      unpack8(*reinterpret_cast<const uint4*>(base + ((long)h0 * w + w1) * ldx), v01);
-      unpack8(*reinterpret_cast<const uint4*>(base + ((long)h1 * w + w0) * ldx), v10);
-      unpack8(*reinterpret_cast<const uint4*>(base + ((long)h1 * w + w1) * ldx), v11);
+      unpack8(*reinterpret_cast<const uint4*>(r0 + (long)w0 * ldx + cg * 8), v00);
+      unpack8(*reinterpret_cast<const uint4*>(r0 + (long)w1 * ldx + cg * 8), v01);
+      unpack8(*reinterpret_cast<const uint4*>(r1 + (long)w0 * ldx + cg * 8), v10);
+      unpack8(*reinterpret_cast<const uint4*>(r1 + (long)w1 * ldx + cg * 8), v11);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         o[j] = lh0 * (lw0 * v00[j] + lw1 * v01[j]) + lh1 * (lw0 * v10[j] + lw1 * v11[j]);
@@ -484,7 +491,7 @@ __global__ void upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, l
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = 0.f;
     }
-    *reinterpret_cast<uint4*>(out + (((long)n * Ho + ho) * Wo + wo) * ldo + cg * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(orow + (long)wo * ldo + cg * 8) = pack8(o);
   }
 }
 
@@ -496,51 +503,67 @@ __device__ __forceinline__ float bilinear_weight(int o, float ratio, int in_size
   return (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
 }
 
-__global__ void upsample2x_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long lddo,
-                                          __nv_bfloat16* __restrict__ dx, long lddx, int N, int h,
-                                          int w, int Ho, int Wo, int CG, int pad_top,
-                                          int pad_left, float rh, float rw) {
-  const long total = (long)N * h * w * CG;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const int cg = i % CG;
-    long t = i / CG;
-    const int wi = t % w; t /= w;
-    const int hi = t % h;
-    const int n = t / h;
-    // candidate upsampled rows/cols whose 2-tap stencil can touch (hi, wi)
-    int oh_lo = 0, oh_hi = 2 * h - 1, ow_lo = 0, ow_hi = 2 * w - 1;
-    if (rh > 0.f) {
-      oh_lo = max(0, (int)floorf((float)(hi - 1) / rh) - 1);
-      oh_hi = min(2 * h - 1, (int)ceilf((float)(hi + 1) / rh) + 1);
+// candidate upsampled indices whose 2-tap stencil can touch source index i (conservative)
+__device__ __forceinline__ void bilinear_candidates(int i, float ratio, int in_size, int& lo, int& hi) {
+  lo = 0;
+  hi = 2 * in_size - 1;
+  if (ratio > 0.f) {
+    lo = max(0, (int)floorf((float)(i - 1) / ratio) - 1);
+    hi = min(2 * in_size - 1, (int)ceilf((float)(i + 1) / ratio) + 1);
+  }
+}
+
+constexpr int kUpMaxTaps = 8;
+
+// Gather-form backward, one block per source row (n, hi): the contributing output rows and
+// their weights are block-uniform (computed once into smem); each thread gathers <= 8 columns.
+__global__ void __launch_bounds__(256)
+upsample2x_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long lddo,
+                          __nv_bfloat16* __restrict__ dx, long lddx, int h, int w, int Ho, int Wo,
+                          int CG, int pad_top, int pad_left, float rh, float rw) {
+  __shared__ int s_rows[kUpMaxTaps];
+  __shared__ float s_wts[kUpMaxTaps];
+  __shared__ int s_cnt;
+  const int row = blockIdx.x;
+  const int n = row / h;
+  const int hi = row - n * h;
+  if (threadIdx.x == 0) {
+    int lo, hi_c, cnt = 0;
+    bilinear_candidates(hi, rh, h, lo, hi_c);
+    for (int oh = lo; oh <= hi_c && cnt < kUpMaxTaps; ++oh) {
+      const float wh = bilinear_weight(oh, rh, h, hi);
+      const int ph = oh + pad_top;
+      if (wh != 0.f && ph >= 0 && ph < Ho) { s_rows[cnt] = ph; s_wts[cnt] = wh; ++cnt; }
     }
-    if (rw > 0.f) {
-      ow_lo = max(0, (int)floorf((float)(wi - 1) / rw) - 1);
-      ow_hi = min(2 * w - 1, (int)ceilf((float)(wi + 1) / rw) + 1);
-    }
+    s_cnt = cnt;
+  }
+  __syncthreads();
+  const int cnt_h = s_cnt;
+  __nv_bfloat16* drow = dx + (long)row * w * lddx;
+  const int work = w * CG;
+  for (int i = threadIdx.x; i < work; i += blockDim.x) {
+    const int wi = i / CG;
+    const int cg = i - wi * CG;
+    int ow_lo, ow_hi;
+    bilinear_candidates(wi, rw, w, ow_lo, ow_hi);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
-      const float wh = bilinear_weight(oh, rh, h, hi);
-      if (wh == 0.f) continue;
-      const int ph = oh + pad_top;
-      if (ph < 0 || ph >= Ho) continue;
-      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-        const float ww = bilinear_weight(ow, rw, w, wi);
-        if (ww == 0.f) continue;
-        const int pw = ow + pad_left;
-        if (pw < 0 || pw >= Wo) continue;
+    for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+      const float ww = bilinear_weight(ow, rw, w, wi);
+      const int pw = ow + pad_left;
+      if (ww == 0.f || pw < 0 || pw >= Wo) continue;
+      for (int t = 0; t < cnt_h; ++t) {
         float g[8];
-        unpack8(*reinterpret_cast<const uint4*>(dout + (((long)n * Ho + ph) * Wo + pw) * lddo +
+        unpack8(*reinterpret_cast<const uint4*>(dout + (((long)n * Ho + s_rows[t]) * Wo + pw) * lddo +
                                                 cg * 8),
                 g);
-        const float wgt = wh * ww;
+        const float wgt = s_wts[t] * ww;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, g[j], acc[j]);
       }
     }
-    *reinterpret_cast<uint4*>(dx + (((long)n * h + hi) * w + wi) * lddx + cg * 8) = pack8(acc);
+    *reinterpret_cast<uint4*>(drow + (long)wi * lddx + cg * 8) = pack8(acc);
   }
 }
 
@@ -703,9 +726,8 @@ int fpb200_upsample2x_pad_concat_fwd(const void* x, long ldx, void* out, long ld
                                      int w, int Ho, int Wo, int C, void* stream) {
   if (C % 8 != 0 || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
   const int pad_top = (Ho - 2 * h) / 2, pad_left = (Wo - 2 * w) / 2;
-  const long total = (long)N * Ho * Wo * (C / 8);
-  upsample2x_pad_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, N, h, w, Ho, Wo, C / 8, pad_top,
+  upsample2x_pad_fwd_kernel<<<N * Ho, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, h, w, Ho, Wo, C / 8, pad_top,
       pad_left, align_corners_ratio(h, 2 * h), align_corners_ratio(w, 2 * w));
   return check_launch("upsample2x_pad_concat_fwd");
 }
@@ -714,9 +736,8 @@ int fpb200_upsample2x_pad_concat_bwd(const void* dout, long lddo, void* dx, long
                                      int h, int w, int Ho, int Wo, int C, void* stream) {
   if (C % 8 != 0 || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
   const int pad_top = (Ho - 2 * h) / 2, pad_left = (Wo - 2 * w) / 2;
-  const long total = (long)N * h * w * (C / 8);
-  upsample2x_pad_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx, N, h, w, Ho, Wo, C / 8, pad_top,
+  upsample2x_pad_bwd_kernel<<<N * h, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx, h, w, Ho, Wo, C / 8, pad_top,
       pad_left, align_corners_ratio(h, 2 * h), align_corners_ratio(w, 2 * w));
   return check_launch("upsample2x_pad_concat_bwd");
 }

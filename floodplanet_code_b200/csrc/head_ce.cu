@@ -55,68 +55,86 @@ head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const float* _
 }
 
 // ---------------------------------------------------------------------------
-// head backward: 8 lanes x 8 channels cover one pixel, 4 pixels per warp iteration.
+// head backward: 8 lanes x 8 channels cover one pixel, 8 pixels (two quads) per warp
+// iteration so that two independent 16-byte loads per lane are in flight.
 //   dx[p, c]  = sum_k dl[k, p] * w[k, c]
 //   dW[k, c] += dl[k, p] * x[p, c],   db[k] += dl[k, p]
 // ---------------------------------------------------------------------------
 constexpr int kHeadBwdThreads = 256;
 
+template <int NC>
 __global__ void __launch_bounds__(kHeadBwdThreads)
 head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, long ldx,
                    const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, long lddx,
                    float* __restrict__ partials, int N, long hw, int ncls) {
-  __shared__ float sw[kMaxClasses * kHeadC];
-  __shared__ float red[(kHeadBwdThreads / 32) * kMaxClasses * (kHeadC + 1)];
-  for (int i = threadIdx.x; i < ncls * kHeadC; i += blockDim.x) sw[i] = w[i];
+  __shared__ float sw[NC * kHeadC];
+  __shared__ float red[(kHeadBwdThreads / 32) * NC * (kHeadC + 1)];
+  for (int i = threadIdx.x; i < NC * kHeadC; i += blockDim.x) sw[i] = i < ncls * kHeadC ? w[i] : 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane >> 3;  // which of the 4 pixels of this warp iteration
+  const int sub = lane >> 3;  // which pixel of a quad
   const int cg = lane & 7;    // channel group: channels cg*8 .. cg*8+7
-  float dw[kMaxClasses][8];
-  float db[kMaxClasses];
+  float wreg[NC][8];
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
+  for (int k = 0; k < NC; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wreg[k][j] = sw[k * kHeadC + cg * 8 + j];
+  float dw[NC][8];
+  float db[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
     db[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw[k][j] = 0.f;
   }
   const long total = (long)N * hw;
   const long warps_total = (long)gridDim.x * (kHeadBwdThreads / 32);
-  for (long base = ((long)blockIdx.x * (kHeadBwdThreads / 32) + warp) * 4; base < total;
-       base += warps_total * 4) {
-    const long px = base + sub;
-    if (px < total) {
-      const long n = px / hw, o = px - n * hw;
-      float dl[kMaxClasses];
+  for (long base = ((long)blockIdx.x * (kHeadBwdThreads / 32) + warp) * 8; base < total;
+       base += warps_total * 8) {
+    long px[2];
+    bool ok[2];
+    uint4 xin[2];
+    float dl[2][NC];
 #pragma unroll
-      for (int k = 0; k < kMaxClasses; ++k)
-        dl[k] = k < ncls ? __ldg(dlogits + ((long)n * ncls + k) * hw + o) : 0.f;
-      float f[8], g[8];
-      unpack8h(__ldg(reinterpret_cast<const uint4*>(x + px * ldx + cg * 8)), f);
+    for (int u = 0; u < 2; ++u) {
+      px[u] = base + u * 4 + sub;
+      ok[u] = px[u] < total;
+      if (ok[u]) {
+        xin[u] = __ldg(reinterpret_cast<const uint4*>(x + px[u] * ldx + cg * 8));
+        const long n = px[u] / hw, o = px[u] - n * hw;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+        for (int k = 0; k < NC; ++k)
+          dl[u][k] = k < ncls ? __ldg(dlogits + ((long)n * ncls + k) * hw + o) : 0.f;
+      }
+    }
 #pragma unroll
-      for (int k = 0; k < kMaxClasses; ++k) {
-        if (k < ncls) {
+    for (int u = 0; u < 2; ++u) {
+      if (ok[u]) {
+        float f[8], g[8];
+        unpack8h(xin[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            g[j] = fmaf(dl[k], sw[k * kHeadC + cg * 8 + j], g[j]);
-            dw[k][j] = fmaf(dl[k], f[j], dw[k][j]);
+            g[j] = fmaf(dl[u][k], wreg[k][j], g[j]);
+            dw[k][j] = fmaf(dl[u][k], f[j], dw[k][j]);
           }
-          db[k] += dl[k];
+          db[k] += dl[u][k];
         }
+        uint4 o4;
+        o4.x = pack_bf16x2(g[0], g[1]);
+        o4.y = pack_bf16x2(g[2], g[3]);
+        o4.z = pack_bf16x2(g[4], g[5]);
+        o4.w = pack_bf16x2(g[6], g[7]);
+        *reinterpret_cast<uint4*>(dx + px[u] * lddx + cg * 8) = o4;
       }
-      uint4 o4;
-      o4.x = pack_bf16x2(g[0], g[1]);
-      o4.y = pack_bf16x2(g[2], g[3]);
-      o4.z = pack_bf16x2(g[4], g[5]);
-      o4.w = pack_bf16x2(g[6], g[7]);
-      *reinterpret_cast<uint4*>(dx + px * lddx + cg * 8) = o4;
     }
   }
   // reduce the 4 pixel sub-lanes of the warp
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
+  for (int k = 0; k < NC; ++k) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       dw[k][j] += __shfl_xor_sync(0xffffffffu, dw[k][j], 8);
@@ -128,17 +146,17 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
   const int stride = kHeadC + 1;
   if (sub == 0) {
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
+    for (int k = 0; k < NC; ++k) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[(warp * kMaxClasses + k) * stride + cg * 8 + j] = dw[k][j];
-      if (cg == 0) red[(warp * kMaxClasses + k) * stride + kHeadC] = db[k];
+      for (int j = 0; j < 8; ++j) red[(warp * NC + k) * stride + cg * 8 + j] = dw[k][j];
+      if (cg == 0) red[(warp * NC + k) * stride + kHeadC] = db[k];
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ncls * stride; i += blockDim.x) {
     const int k = i / stride, c = i - k * stride;
     float acc = 0.f;
-    for (int wv = 0; wv < kHeadBwdThreads / 32; ++wv) acc += red[(wv * kMaxClasses + k) * stride + c];
+    for (int wv = 0; wv < kHeadBwdThreads / 32; ++wv) acc += red[(wv * NC + k) * stride + c];
     partials[(size_t)blockIdx.x * ncls * stride + i] = acc;
   }
 }
@@ -313,7 +331,7 @@ int fpb200_head1x1_fwd(const void* x, long ldx, const float* w, const float* b, 
   return check_launch("head1x1_fwd");
 }
 
-int fpb200_head_bwd_rows(void) { return 4 * sm_count(); }
+int fpb200_head_bwd_rows(void) { return 8 * sm_count(); }
 
 int fpb200_head1x1_bwd(const float* dlogits, const void* x, long ldx, const float* w, void* dx,
                        long lddx, float* dw, float* db, float* partials, int N, int H, int W,
@@ -321,9 +339,14 @@ int fpb200_head1x1_bwd(const float* dlogits, const void* x, long ldx, const floa
   if (C != kHeadC || n_classes < 1 || n_classes > kMaxClasses || ldx % 8 != 0 || lddx % 8 != 0)
     return FPB200_ERR_SHAPE;
   const int rows = fpb200_head_bwd_rows();
-  head1x1_bwd_kernel<<<rows, kHeadBwdThreads, 0, (cudaStream_t)stream>>>(
-      dlogits, (const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)dx, lddx, partials, N,
-      (long)H * W, n_classes);
+  if (n_classes <= 4)
+    head1x1_bwd_kernel<4><<<rows, kHeadBwdThreads, 0, (cudaStream_t)stream>>>(
+        dlogits, (const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)dx, lddx, partials, N,
+        (long)H * W, n_classes);
+  else
+    head1x1_bwd_kernel<8><<<rows, kHeadBwdThreads, 0, (cudaStream_t)stream>>>(
+        dlogits, (const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)dx, lddx, partials, N,
+        (long)H * W, n_classes);
   int rc = check_launch("head1x1_bwd");
   if (rc != FPB200_OK) return rc;
   const int n = n_classes * (kHeadC + 1);

@@ -77,31 +77,33 @@ def trainable_keys(sd: Dict[str, torch.Tensor]) -> List[str]:
 
 
 def _bf16(t: torch.Tensor) -> torch.Tensor:
-    return t.to(torch.bfloat16).to(torch.float32)
+    """Round to bf16 and back (straight-through for autograd: d round(t)/dt := 1)."""
+    return t + (t.detach().to(torch.bfloat16).to(torch.float32) - t.detach())
 
 
 def _conv_bn_relu_bf16(x, sd, conv, bn, training: bool):
     """Same layer with the CUDA path's storage precision emulated (NOT the reference's
     arithmetic -- a diagnostic that separates kernel bugs from bf16 rounding): bf16 conv
-    operands, fp32 accumulation, statistics from the fp32 accumulators, normalisation applied
-    to the bf16-stored conv output, bf16-stored activation.  The conv bias only shifts the
-    batch mean, so it is kept out of the GEMM exactly like the kernels do."""
-    y = F.conv2d(x, _bf16(sd[f"{conv}.weight"]), None, padding=1)
+    operands, fp32 accumulation, the conv output stored in bf16, BatchNorm statistics and
+    normalisation taken from those stored values, bf16-stored activation.  The conv bias only
+    shifts the batch mean, so it is kept out of the GEMM exactly like the kernels do.
+    Rounding is straight-through, so autograd gives the gradients an exact-arithmetic backward
+    pass would produce AT THE SAME (bf16) activations and ReLU masks."""
+    y = _bf16(F.conv2d(x, _bf16(sd[f"{conv}.weight"]), None, padding=1))
     if training:
         sd[f"{bn}.num_batches_tracked"] += 1
-        mean = y.mean((0, 2, 3))
-        var = y.var((0, 2, 3), unbiased=False)
-        n = y.numel() / y.shape[1]
         with torch.no_grad():
+            mean = y.mean((0, 2, 3))
+            var = y.var((0, 2, 3), unbiased=False)
+            n = y.numel() / y.shape[1]
             sd[f"{bn}.running_mean"].mul_(0.9).add_(0.1 * (mean + sd[f"{conv}.bias"]))
             sd[f"{bn}.running_var"].mul_(0.9).add_(0.1 * var * n / max(n - 1, 1))
-        scale = sd[f"{bn}.weight"] * torch.rsqrt(var + 1e-5)
-        shift = sd[f"{bn}.bias"] - mean * scale
-        y = _bf16(y)
+        out = F.batch_norm(y, None, None, sd[f"{bn}.weight"], sd[f"{bn}.bias"], True, 0.1, 1e-5)
     else:
         scale = sd[f"{bn}.weight"] / torch.sqrt(sd[f"{bn}.running_var"] + 1e-5)
         shift = sd[f"{bn}.bias"] + (sd[f"{conv}.bias"] - sd[f"{bn}.running_mean"]) * scale
-    return _bf16(F.relu(y * scale[None, :, None, None] + shift[None, :, None, None]))
+        out = y * scale[None, :, None, None] + shift[None, :, None, None]
+    return _bf16(F.relu(out))
 
 
 _EMULATE_BF16 = False
@@ -185,15 +187,16 @@ def masked_ce(logits: torch.Tensor, target: torch.Tensor, ignore_index: Optional
 
 
 def training_step(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor],
-                  ignore_index: Optional[int], early_fusion: bool = True):
+                  ignore_index: Optional[int], early_fusion: bool = True, emulate_bf16: bool = False):
     """Forward + loss + backward of one reference training step (water_seg_model.py:98-136 and
-    the ``loss.backward()`` Lightning runs).  Returns (loss, pred, logits, {name: grad})."""
+    the ``loss.backward()`` Lightning runs).  Returns (loss, pred, logits, {name: grad}).
+    ``emulate_bf16`` switches to the storage-precision diagnostic (see _conv_bn_relu_bf16)."""
     keys = trainable_keys(sd)
     for k in keys:
         sd[k].requires_grad_(True)
         sd[k].grad = None
     x = early_fusion_input(batch) if early_fusion else batch['image']
-    logits = unet_forward(sd, x, training=True)
+    logits = unet_forward_bf16_emulated(sd, x, True) if emulate_bf16 else unet_forward(sd, x, training=True)
     loss, pred = masked_ce(logits, batch['target'], ignore_index)
     loss.backward()
     grads = {k: (sd[k].grad.detach().clone() if sd[k].grad is not None else torch.zeros_like(sd[k]))

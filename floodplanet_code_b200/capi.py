@@ -19,6 +19,7 @@ _vp, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_double
 SIGNATURES = {
     "fpb200_abi_version": (_i, []),
     "fpb200_ingest_nchw_f32_to_nhwc_bf16": (_i, [C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _i, _i, _i, _vp]),
+    "fpb200_ingest_scene_tiles": (_i, [_vp, _i, _l, _l, _vp, _i, _i, _i, _vp, _i, _vp]),
     "fpb200_repack_weights_fprop": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "fpb200_repack_weights_dgrad": (_i, [_vp, _vp, _i, _i, _vp]),
     "fpb200_conv_stat_rows": (_i, []),
@@ -43,6 +44,8 @@ SIGNATURES = {
     "fpb200_ce_rows": (_i, []),
     "fpb200_softmax_ce_argmax_fwd": (_i, [_vp, _vp, _l, _vp, _vp, _vp, _vp, _i, _i, _l, _vp]),
     "fpb200_softmax_ce_bwd": (_i, [_vp, _vp, _l, _vp, _vp, _vp, _i, _i, _l, _vp]),
+    "fpb200_softmax_stitch_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _l, _l, _vp]),
+    "fpb200_canvas_to_mask_u8": (_i, [_vp, _vp, _vp, _l, _i, _vp]),
     "fpb200_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
 }
 

@@ -83,6 +83,33 @@ __global__ void ingest_kernel(IngestArgs a, __nv_bfloat16* __restrict__ dst, int
   }
 }
 
+// Tiles of one resident scene [C][H][W] f32 -> NHWC bf16 [n][th][tw][c_pad]; pixels outside the
+// scene or outside the tile's valid extent are zero (the dataset pads remainder crops).
+__global__ void ingest_scene_tiles_kernel(const float* __restrict__ scene, int C, long H, long W,
+                                          const int* __restrict__ tiles, int n, int th, int tw,
+                                          __nv_bfloat16* __restrict__ dst, int c_pad) {
+  const long hw = (long)th * tw;
+  const long total = (long)n * hw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / hw);
+    const long o = i - (long)t * hw;
+    const int y = (int)(o / tw), x = (int)(o - (long)y * tw);
+    const int h0 = tiles[t * 4 + 0], w0 = tiles[t * 4 + 1], hh = tiles[t * 4 + 2], ww = tiles[t * 4 + 3];
+    const long gy = h0 + y, gx = w0 + x;
+    const bool in = y < hh && x < ww && gy < H && gx < W;
+    for (int g = 0; g < c_pad; g += 8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g + j;
+        f[j] = (in && c < C) ? __ldg(scene + ((long)c * H + gy) * W + gx) : 0.f;
+      }
+      *reinterpret_cast<uint4*>(dst + i * c_pad + g) = pack8(f);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // weight repack
 // ---------------------------------------------------------------------------
@@ -617,6 +644,15 @@ int fpb200_ingest_nchw_f32_to_nhwc_bf16(const float* const* srcs, const int* src
   ingest_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       a, (__nv_bfloat16*)dst, c_pad, N, (long)H * W);
   return check_launch("ingest");
+}
+
+int fpb200_ingest_scene_tiles(const float* scene, int C, long H, long W, const int* tiles,
+                              int n_tiles, int th, int tw, void* dst, int c_pad, void* stream) {
+  if (c_pad % 8 != 0 || c_pad > 64 || C > c_pad || n_tiles < 1) return FPB200_ERR_SHAPE;
+  const long total = (long)n_tiles * th * tw;
+  ingest_scene_tiles_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      scene, C, H, W, tiles, n_tiles, th, tw, (__nv_bfloat16*)dst, c_pad);
+  return check_launch("ingest_scene_tiles");
 }
 
 int fpb200_repack_weights_fprop(const float* w_oihw, void* w_packed, int Cout, int Cin,

@@ -313,6 +313,63 @@ softmax_ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restric
   }
 }
 
+// ---------------------------------------------------------------------------
+// sliding-window inference post-processing (infer.py:122-184, utils_image.py:410-494):
+// softmax over classes, scatter-add of tile probabilities + weights into the scene canvas,
+// then canvas/(w+1e-5) -> argmax -> clip(0,1)*255 as uint8.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_stitch_add_kernel(const float* __restrict__ logits, float* __restrict__ canvas,
+                          float* __restrict__ weight, const int* __restrict__ tiles, int n, int ncls,
+                          int th, int tw, long H, long W) {
+  const long hw = (long)th * tw;
+  const long total = (long)n * hw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / hw);
+    const long o = i - (long)t * hw;
+    const int y = (int)(o / tw), x = (int)(o - (long)y * tw);
+    const int h0 = tiles[t * 4 + 0], w0 = tiles[t * 4 + 1], hh = tiles[t * 4 + 2], ww = tiles[t * 4 + 3];
+    const long gy = h0 + y, gx = w0 + x;
+    if (y >= hh || x >= ww || gy >= H || gx >= W) continue;
+    float l[kMaxClasses];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < ncls) { l[k] = __ldg(logits + ((long)t * ncls + k) * hw + o); mx = fmaxf(mx, l[k]); }
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < ncls) { l[k] = expf(l[k] - mx); se += l[k]; }
+    const float inv = 1.f / se;
+    float* dst = canvas + (gy * W + gx) * ncls;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < ncls) atomicAdd(dst + k, l[k] * inv);
+    atomicAdd(weight + gy * W + gx, 1.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+canvas_to_mask_kernel(const float* __restrict__ canvas, const float* __restrict__ weight,
+                      uint8_t* __restrict__ mask, long npix, int ncls) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < npix;
+       i += (long)gridDim.x * blockDim.x) {
+    const float inv = 1.f / (weight[i] + 1e-5f);
+    float best = 0.f;
+    int bi = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      if (k < ncls) {
+        float v = canvas[i * ncls + k] * inv;
+        if (v != v) v = 0.f;  // np.nan_to_num
+        if (k == 0 || v > best) { best = v; bi = k; }
+      }
+    }
+    mask[i] = bi >= 1 ? 255 : 0;  // np.clip(argmax, 0, 1) * 255
+  }
+}
+
 }  // namespace fp
 
 using namespace fp;
@@ -384,6 +441,27 @@ int fpb200_softmax_ce_bwd(const float* logits, const int64_t* target, long ignor
   softmax_ce_bwd_kernel<<<(int)g, kCeThreads, 0, (cudaStream_t)stream>>>(
       logits, target, ignore_index, result, grad_out, dlogits, N, n_classes, hw);
   return check_launch("softmax_ce_bwd");
+}
+
+int fpb200_softmax_stitch_add(const float* logits, float* canvas, float* weight, const int* tiles,
+                              int n_tiles, int n_classes, int th, int tw, long H, long W,
+                              void* stream) {
+  if (n_classes < 1 || n_classes > kMaxClasses || n_tiles < 1) return FPB200_ERR_SHAPE;
+  const long total = (long)n_tiles * th * tw;
+  long g = (total + 255) / 256;
+  if (g > 148L * 16) g = 148L * 16;
+  softmax_stitch_add_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(logits, canvas, weight, tiles,
+                                                                      n_tiles, n_classes, th, tw, H, W);
+  return check_launch("softmax_stitch_add");
+}
+
+int fpb200_canvas_to_mask_u8(const float* canvas, const float* weight, uint8_t* mask, long npix,
+                             int n_classes, void* stream) {
+  if (n_classes < 1 || n_classes > kMaxClasses) return FPB200_ERR_SHAPE;
+  long g = (npix + 255) / 256;
+  if (g > 148L * 16) g = 148L * 16;
+  canvas_to_mask_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(canvas, weight, mask, npix, n_classes);
+  return check_launch("canvas_to_mask_u8");
 }
 
 }  // extern "C"

@@ -183,23 +183,31 @@ class UNetEngine:
         self.conv_events.append((tag, i, 2.0 * n * hw * s.cout * 9 * s.cin, e0, e1))
 
     # -------------------------------------------------------------------------------------
-    def forward(self, images: Sequence[torch.Tensor], params: Dict[str, torch.Tensor],
-                buffers: Dict[str, torch.Tensor], training: bool, save: bool):
-        """images: list of NCHW fp32 tensors (concatenated along C in order).
-        Returns (logits fp32 NCHW, ForwardState or None)."""
-        dev = images[0].device
-        n, _, h, w = images[0].shape
-        if sum(int(t.shape[1]) for t in images) != self.n_channels:
-            raise RuntimeError(
-                f"floodplanet_b200: expected {self.n_channels} input channels, got "
-                f"{[int(t.shape[1]) for t in images]}")
+    def forward(self, images: Optional[Sequence[torch.Tensor]], params: Dict[str, torch.Tensor],
+                buffers: Dict[str, torch.Tensor], training: bool, save: bool,
+                ingested: Optional[torch.Tensor] = None):
+        """images: list of NCHW fp32 tensors (concatenated along C in order), or `ingested`: an
+        already channel-padded NHWC bf16 batch (tile-sharded inference ingests straight from the
+        resident scene).  Returns (logits fp32 NCHW, ForwardState or None)."""
+        if ingested is not None:
+            dev = ingested.device
+            n, h, w, cp = ingested.shape
+            if cp != self.cin_pad:
+                raise RuntimeError(f"floodplanet_b200: ingested batch has {cp} channels, expected {self.cin_pad}")
+        else:
+            dev = images[0].device
+            n, _, h, w = images[0].shape
+            if sum(int(t.shape[1]) for t in images) != self.n_channels:
+                raise RuntimeError(
+                    f"floodplanet_b200: expected {self.n_channels} input channels, got "
+                    f"{[int(t.shape[1]) for t in images]}")
         sizes = self._level_sizes(h, w)
         bf = dict(dtype=torch.bfloat16, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         st = ForwardState(n=n, sizes=sizes) if save else None
         launches = 0
 
-        x = ops.ingest(images, self.cin_pad)
+        x = ingested if ingested is not None else ops.ingest(images, self.cin_pad)
         launches += 1
 
         # concat buffers for the four Up stages: [skip | upsampled], at levels 3,2,1,0

@@ -1,0 +1,100 @@
+"""Tile-sharded sliding-window inference over one scene (BASELINE.json configs[4]).
+
+What the reference does per scene (infer.py:64-184; predict.py uses ``cfg.crop_stride``):
+enumerate crops with ``get_crop_slices(..., mode='exact')`` (datasets/utils.py:86-212), run the
+model in eval mode on batches of crops, softmax the fp32 logits on the host, scatter-add them
+into a canvas with a weight canvas (utils_image.py:410-494), divide by ``w + 1e-5``, and write
+``np.clip(argmax, 0, 1) * 255`` as uint8.
+
+Here the scene stays resident in HBM, crops are ingested straight from it (NCHW f32 ->
+NHWC bf16, zero padded at the ragged edges), the UNet runs the folded-BatchNorm eval path, and
+softmax / stitch / normalise / argmax / clip are two more kernels on the device.  Tiles are
+independent, so N GPUs take contiguous ranges of the tile list with no data-path collective;
+only the final uint8 masks (or, for overlapping strides, the canvases) are combined.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .parallel import shard_range
+from .unet import UNet
+
+
+def crop_slices(height: int, width: int, crop_height: int, crop_width: int, step=None) -> List[List[int]]:
+    """Tile list of the reference's 'exact' mode: full crops on the stride grid, then the right
+    remainder column, the bottom remainder row, the corner -- each as [h0, w0, h, w].  Keeps the
+    reference's quirk of using crop_height as the width of bottom-remainder tiles
+    (datasets/utils.py:203); a tile never extends the scene, extents are clipped when stitched."""
+    if step is None:
+        hs, ws = crop_height, crop_width
+    elif isinstance(step, tuple):
+        hs, ws = int(step[0]), int(step[1])
+    else:
+        hs = ws = int(step)
+    if hs <= 0 or ws <= 0:
+        raise ValueError(f"Step of size {min(hs, ws)} is too small.")
+    if hs > height or ws > width:
+        raise ValueError(f"Step ({hs}, {ws}) is too large for image ({height}, {width})")
+    nh = (height - crop_height) // hs + 1 if height >= crop_height else 0
+    nw = (width - crop_width) // ws + 1 if width >= crop_width else 0
+    tiles = [[i * hs, j * ws, crop_height, crop_width] for i in range(nh) for j in range(nw)]
+    rem_h, rem_w = height - nh * hs, width - nw * ws
+    if rem_w != 0:
+        tiles += [[i * hs, nw * ws, crop_height, rem_w] for i in range(nh)]
+    if rem_h != 0:
+        tiles += [[nh * hs, j * ws, rem_h, crop_height] for j in range(nw)]
+    if rem_h != 0 and rem_w != 0:
+        tiles.append([nh * hs, nw * ws, rem_h, rem_w])
+    return tiles
+
+
+@torch.no_grad()
+def predict_scene(unet: UNet, scene: torch.Tensor, crop: int = 512, stride: Optional[int] = None,
+                  tile_batch: int = 32, rank: int = 0, world: int = 1, combine: bool = True):
+    """Water mask (uint8 [H, W], values 0 / 255) of one scene [C, H, W] fp32.
+
+    Each rank processes ``shard_range(n_tiles, rank, world)``.  With ``combine`` and an
+    initialised process group the per-rank results are merged (canvases summed for overlapping
+    strides, masks max-reduced otherwise); without it the caller gets this rank's partial mask.
+    Returns (mask, n_tiles_processed, kernel_launches).
+    """
+    if not scene.is_cuda:
+        raise RuntimeError("predict_scene: the scene must be resident on the CUDA device (no CPU fallback)")
+    if unet.training:
+        raise RuntimeError("predict_scene: call model.eval() first (reference: _set_model_to_eval)")
+    c, H, W = scene.shape
+    stride = crop if stride is None else stride
+    tiles_all = crop_slices(H, W, crop, crop, stride)
+    mine = [tiles_all[i] for i in shard_range(len(tiles_all), rank, world)]
+    engine = unet._engine
+    params = dict(unet.named_parameters())
+    buffers = dict(unet.named_buffers())
+    ncls = unet.n_classes
+    dev = scene.device
+    canvas = torch.zeros((H, W, ncls), dtype=torch.float32, device=dev)
+    weight = torch.zeros((H, W), dtype=torch.float32, device=dev)
+    scene = scene.contiguous()
+    launches = 0
+    for b0 in range(0, len(mine), tile_batch):
+        chunk = mine[b0:b0 + tile_batch]
+        # valid extents are clipped to the scene (the stitcher slices canvas[h0:hE, w0:wE])
+        meta = [[h0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
+        tdev = torch.tensor(meta, dtype=torch.int32, device=dev)
+        x = ops.ingest_scene_tiles(scene, tdev, crop, crop, engine.cin_pad)
+        logits, _ = engine.forward(None, params, buffers, training=False, save=False, ingested=x)
+        ops.softmax_stitch_add(logits, canvas, weight, tdev)
+        launches += engine.launches + 1
+    overlapping = stride < crop
+    distributed = combine and world > 1 and torch.distributed.is_initialized()
+    if distributed and overlapping:
+        torch.distributed.all_reduce(canvas)
+        torch.distributed.all_reduce(weight)
+    mask = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    ops.canvas_to_mask_u8(canvas, weight, mask)
+    launches += 1
+    if distributed and not overlapping:
+        torch.distributed.all_reduce(mask, op=torch.distributed.ReduceOp.MAX)
+    return mask, len(mine), launches

@@ -297,3 +297,31 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0) -> None:
     st = _lib().fpb200_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
                                  beta1, beta2, eps, step, grad_scale, _stream())
     capi.check(st, "adam_step", n=p.numel())
+
+
+# ------------------------------------------------------------------------------------------
+def ingest_scene_tiles(scene: torch.Tensor, tiles: torch.Tensor, th: int, tw: int, c_pad: int) -> torch.Tensor:
+    """scene [C,H,W] fp32 (device) + tiles int32 [n,4] (device: h0,w0,valid_h,valid_w) -> NHWC bf16."""
+    _require_cuda(scene, tiles)
+    c, h, w = scene.shape
+    n = tiles.shape[0]
+    out = torch.empty((n, th, tw, c_pad), dtype=torch.bfloat16, device=scene.device)
+    st = _lib().fpb200_ingest_scene_tiles(scene.data_ptr(), c, h, w, tiles.data_ptr(), n, th, tw,
+                                          out.data_ptr(), c_pad, _stream())
+    capi.check(st, "ingest_scene_tiles", C=c, H=h, W=w, n_tiles=n, th=th, tw=tw)
+    return out
+
+
+def softmax_stitch_add(logits, canvas, weight, tiles) -> None:
+    n, ncls, th, tw = logits.shape
+    h, w = weight.shape
+    st = _lib().fpb200_softmax_stitch_add(logits.data_ptr(), canvas.data_ptr(), weight.data_ptr(),
+                                          tiles.data_ptr(), n, ncls, th, tw, h, w, _stream())
+    capi.check(st, "softmax_stitch_add", n_tiles=n, n_classes=ncls, th=th, tw=tw, H=h, W=w)
+
+
+def canvas_to_mask_u8(canvas, weight, mask) -> None:
+    h, w = weight.shape
+    st = _lib().fpb200_canvas_to_mask_u8(canvas.data_ptr(), weight.data_ptr(), mask.data_ptr(), h * w,
+                                         canvas.shape[2], _stream())
+    capi.check(st, "canvas_to_mask_u8", H=h, W=w, n_classes=canvas.shape[2])

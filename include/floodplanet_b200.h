@@ -48,6 +48,13 @@ int fpb200_ingest_nchw_f32_to_nhwc_bf16(const float* const* srcs, const int* src
                                         int n_src, void* dst, int c_pad, int N, int H, int W,
                                         void* stream);
 
+/* Sliding-window inference ingest: `n_tiles` crops of ONE scene resident on the device
+ * ([C][H][W] fp32) -> NHWC bf16 [n_tiles][th][tw][c_pad].  `tiles` is a DEVICE int32 array
+ * [n_tiles][4] = (h0, w0, valid_h, valid_w) as produced by get_crop_slices(mode='exact')
+ * (datasets/utils.py:86-212); pixels beyond the valid extent / scene edge are zero padded. */
+int fpb200_ingest_scene_tiles(const float* scene, int C, long H, long W, const int* tiles,
+                              int n_tiles, int th, int tw, void* dst, int c_pad, void* stream);
+
 /* Conv weight repack, OIHW fp32 [Cout][Cin][3][3] ->
  *   fprop packing  bf16 [Cout][9][cin_pad]            (K-major GEMM B operand)
  *   dgrad packing  bf16 [cin_pad_out][9][Cout]  with the filter rotated by 180 degrees
@@ -195,6 +202,20 @@ int fpb200_softmax_ce_argmax_fwd(const float* logits, const int64_t* target, lon
 int fpb200_softmax_ce_bwd(const float* logits, const int64_t* target, long ignore_index,
                           const double* result, const float* grad_out, float* dlogits, int N,
                           int n_classes, long hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sliding-window inference post-processing  -- infer.py:122-184, utils/utils_image.py:410-494
+ * ---------------------------------------------------------------------------------------- */
+
+/* canvas[h0+y, w0+x, :] += softmax(logits[t, :, y, x]); weight[h0+y, w0+x] += 1 for every valid
+ * pixel of every tile (logits fp32 [n_tiles][C][th][tw], canvas fp32 [H][W][C], weight fp32
+ * [H][W], tiles as in fpb200_ingest_scene_tiles). */
+int fpb200_softmax_stitch_add(const float* logits, float* canvas, float* weight, const int* tiles,
+                              int n_tiles, int n_classes, int th, int tw, long H, long W,
+                              void* stream);
+/* mask = clip(argmax_c(nan_to_num(canvas / (weight + 1e-5))), 0, 1) * 255  (uint8 [H][W]). */
+int fpb200_canvas_to_mask_u8(const float* canvas, const float* weight, uint8_t* mask, long npix,
+                             int n_classes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimiser (water_seg_model.py:198-205, optim.Adam defaults) and misc

@@ -72,8 +72,8 @@ struct HaloCfg {
   static constexpr int kABytes = kBoxRows * kRowBytes;             // bytes the TMA writes
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;    // ring pitch
   static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kNB = BN >= 128 ? 7 : 8;                    // weight ring depth
-  static constexpr int kStageOut = 4 * 4096;                       // epilogue staging, 4 KB per warp
+  static constexpr int kNB = BN >= 128 ? 6 : 8;                    // weight ring depth
+  static constexpr int kStageOut = 4 * 2 * 4096;                   // epilogue staging: 2 x 4 KB per warp
   static constexpr int kBudget = 212 * 1024;
   static constexpr int kNARaw = (kBudget - kStageOut - kNB * kBBytes) / kASlot;
   static constexpr int kNA = kNARaw > 4 ? 4 : kNARaw;
@@ -169,7 +169,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop with warp-uniform values (so addresses/descriptors live in
+    // uniform registers); only the tcgen05 instructions are issued by one elected lane.
+    const bool leader = elect_one();
+    {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -197,18 +200,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int k = 0; k < KCH / 16; ++k) {
                 // tap shift (r, s), tile half t and K slice k are compile-time byte offsets
                 const uint32_t a_off = (uint32_t(r * kBox + t * 8 + s) * kRB + k * 32) >> 4;
-                umma_bf16(d_tmem + t * BN, smem_desc_join(a_lo + a_off, kAHi),
-                          smem_desc_join(b_lo + ((k * 32) >> 4), kBHi), kIdesc,
-                          (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
+                if (leader)
+                  umma_bf16(d_tmem + t * BN, smem_desc_join(a_lo + a_off, kAHi),
+                            smem_desc_join(b_lo + ((k * 32) >> 4), kBHi), kIdesc,
+                            (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
               }
             }
-            umma_commit(bempty(sb));
+            if (leader) umma_commit(bempty(sb));
             if (++sb == kNB) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(aempty(sa));
+          if (leader) umma_commit(aempty(sa));
           if (++sa == kNA) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(tfull(as));
+        if (leader) umma_commit(tfull(as));
       }
     }
   } else {
@@ -222,8 +226,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp - 2;
     const bool do_stats = p.stat_partials != nullptr;
     const bool do_affine = p.scale != nullptr;
-    const uint32_t stg = stg_base + ew * 4096;
-    const uint32_t stg_row = stg + lane * 128;
+    const uint32_t stg0 = stg_base + ew * 8192;   // two 4 KB staging tiles, used alternately
+    uint32_t stg_sel = 0;
     constexpr int kUnits = BN / 64;
     float acc_sum[kUnits][2], acc_sq[kUnits][2];
 #pragma unroll
@@ -261,8 +265,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
         for (int u = 0; u < kUnits; ++u) {
-          // the previous TMA store must have finished reading the staging tile
-          if (lane == 0) tma_store_wait_read();
+          // the TMA store issued two units ago must have finished reading this staging tile
+          const uint32_t stg = stg0 + stg_sel * 4096;
+          const uint32_t stg_row = stg + lane * 128;
+          stg_sel ^= 1u;
+          if (lane == 0) tma_store_wait_read_keep1();
           __syncwarp();
 #pragma unroll
           for (int hlf = 0; hlf < 2; ++hlf) {

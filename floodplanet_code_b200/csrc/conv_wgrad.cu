@@ -156,7 +156,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform loop (descriptors in uniform registers); one elected lane issues tcgen05
+    const bool leader = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -186,14 +188,15 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
                      ((uint32_t(wg_pair_lbo_rows(g) * 128) >> 4) << 16);
               b_lo = (b_addr16 + ((k * kWgTW * kBRow) >> 4)) | (1u << 16);
             }
-            umma_bf16(tmem_base + g * Cfg::kN, smem_desc_join(a_lo, kAHi),
-                      smem_desc_join(b_lo, kBHi), kIdesc, k == 0 ? acc : 1u);
+            if (leader)
+              umma_bf16(tmem_base + g * Cfg::kN, smem_desc_join(a_lo, kAHi),
+                        smem_desc_join(b_lo, kBHi), kIdesc, k == 0 ? acc : 1u);
           }
         }
-        umma_commit(empty_bar(stage));
+        if (leader) umma_commit(empty_bar(stage));
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(accum_bar);
+      if (leader) umma_commit(accum_bar);
     }
   } else {
     const int quad = warp & 3;
@@ -281,12 +284,19 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl) {
   pl->tiles_w = (W + kWgTW - 1) / kWgTW;
   pl->tiles_h = (H + kWgTH - 1) / kWgTH;
   pl->num_pix_tiles = N * pl->tiles_h * pl->tiles_w;
-  // split-K so that ~2 waves of CTAs exist, but never more splits than pixel tiles
-  int ks = (2 * sm_count() + pl->n_items - 1) / pl->n_items;
-  if (ks < 1) ks = 1;
-  if (ks > pl->num_pix_tiles) ks = pl->num_pix_tiles;
-  if (ks > 512) ks = 512;
-  pl->ksplit = ks;
+  // split-K: one CTA per SM (smem-limited), so pick the split count whose CTA total fills
+  // whole waves of the 148 SMs best, preferring fewer waves (less partial-sum traffic)
+  const int sms = sm_count();
+  int best_ks = 1;
+  double best_eff = 0.0;
+  for (int ks = 1; ks <= 512 && ks <= pl->num_pix_tiles; ++ks) {
+    const long ctas = (long)pl->n_items * ks;
+    const long waves = (ctas + sms - 1) / sms;
+    if (waves > 3) break;
+    const double eff = (double)ctas / (double)(waves * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best_ks = ks; }
+  }
+  pl->ksplit = best_ks;
   return FPB200_OK;
 }
 

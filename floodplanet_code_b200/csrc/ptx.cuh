@@ -118,6 +118,10 @@ __device__ __forceinline__ void tma_store_commit() {
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// ... all but the most recent one
+__device__ __forceinline__ void tma_store_wait_read_keep1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }

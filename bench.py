@@ -197,8 +197,24 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_pool[0].values())
 
     launches = {"n": 0}
+    use_graph = world == 1 and args.graph
+    graphed = None
+    if use_graph:
+        from floodplanet_code_b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, pool[0], warmup_steps=max(1, args.warmup))
+
+    def graph_step(batch):
+        """Replay of the captured step; the batch is copied into the graph's static inputs
+        (device-to-device for `value`; the e2e path copies host->device straight into them)."""
+        if batch is not graphed.batch:
+            for k, v in graphed.batch.items():
+                v.copy_(batch[k], non_blocking=True)
+        launches["n"] += graphed.kernel_launches
+        return graphed.replay()
 
     def train_step(batch, i):
+        if graphed is not None:
+            return graph_step(batch)
         opt.zero_grad()
         loss = model.training_step(batch, i)
         fwd_launches = engine.launches
@@ -239,7 +255,26 @@ def run_ours(args):
     ms_per_step = elapsed_ms / args.steps
     value = B * world * args.steps / (elapsed_ms / 1000.0)
 
-    # per-kernel-family roofline from the events recorded inside the timed region
+    # per-kernel-family roofline.  Eager mode: the events were recorded inside the timed region.
+    # Graph mode: individual launches inside a replay cannot be bracketed by events, so the
+    # same K steps are run once more, eagerly and instrumented, right after the timed region.
+    instrumented_ms_per_step = ms_per_step
+    if graphed is not None:
+        keep, graphed_ref = graphed, None
+        graphed = None                      # train_step() falls back to eager launches
+        for i in range(2):
+            train_step(pool[i % len(pool)], i)
+        engine.conv_events = []
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            train_step(pool[i % len(pool)], i)
+        e1.record()
+        barrier()
+        instrumented_ms_per_step = e0.elapsed_time(e1) / args.steps
+        conv_events = engine.conv_events
+        engine.conv_events = None
+        graphed = keep
     peaks, peak_src = measured_peaks()
     fam = {}
     for tag, layer, flops, a, b_ in conv_events:
@@ -268,16 +303,21 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": kname, "achieved": roof_all[dom]["achieved"], "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": roof_all[dom]["frac"], "traffic": None,
                     "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-                    "share_of_step": roof_all[dom]["ms_per_step"] / ms_per_step,
+                    "share_of_step": roof_all[dom]["ms_per_step"] / instrumented_ms_per_step,
+                    "timed_with": ("events around every conv launch, eager instrumented pass of the same "
+                                   f"{args.steps} steps ({instrumented_ms_per_step:.2f} ms/step) after the "
+                                   "graph-replayed timed region") if graphed is not None else
+                                  "events around every conv launch inside the timed region",
                     "families": roof_all,
                     "all_conv": {"achieved": conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms else 0.0,
-                                 "share_of_step": conv_ms / args.steps / ms_per_step},
+                                 "share_of_step": conv_ms / args.steps / instrumented_ms_per_step},
                     "worst_layers": sorted(((k, v["flops"] / (v["ms"] / 1000.0) / 1e12, v["ms"] / args.steps)
                                             for k, v in per_layer.items()), key=lambda x: -x[2])[:8]}
 
     # ---------------- phase B: end to end from pinned host memory ----------------
     copy_stream = torch.cuda.Stream(device=dev)
     dev_slots = [{k: torch.empty_like(v, device=dev) for k, v in host_pool[0].items()} for _ in range(2)]
+    # (graph mode: the step consumes slot -> static-input copies enqueued on the compute stream)
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
@@ -337,6 +377,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "cuda_graph": graphed is not None,
             "final_loss": losses[-1] if losses else None,
             "grad_buckets_per_step": reducer.buckets_last_step if reducer else 0,
         }
@@ -357,6 +398,9 @@ def main():
     ap.add_argument("--pool", type=int, default=2, help="distinct synthetic batches cycled through")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the whole step from one CUDA graph (measured: no gain at batch 64, where every "
+                         "kernel is long enough to hide its launch; useful for small batches)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "fpb200_softmax_stitch_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _l, _l, _vp]),
     "fpb200_canvas_to_mask_u8": (_i, [_vp, _vp, _vp, _l, _i, _vp]),
     "fpb200_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
+    "fpb200_adam_step_graphable": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _vp, _f, _vp]),
 }
 
 _ERRORS = {

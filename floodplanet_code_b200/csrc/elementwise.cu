@@ -597,10 +597,17 @@ upsample2x_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long lddo,
 // ---------------------------------------------------------------------------
 // Adam
 // ---------------------------------------------------------------------------
+// step_dev (nullable): device-resident step counter, so the launch is CUDA-graph replayable;
+// the LAST block to finish increments it (threadfence + atomic ticket).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, long n, float lr,
                             float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
-                            float grad_scale) {
+                            float grad_scale, int* step_dev, unsigned int* ticket) {
+  if (step_dev != nullptr) {
+    const float t = (float)(*step_dev + 1);
+    bc1 = 1.f - powf(beta1, t);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  }
   const float step_size = lr / bc1;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
        i += (long)gridDim.x * blockDim.x) {
@@ -611,6 +618,16 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] -= step_size * (mi / denom);
+  }
+  if (step_dev != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        *ticket = 0u;
+        *step_dev += 1;
+      }
+    }
   }
 }
 
@@ -784,8 +801,18 @@ int fpb200_adam_step(float* p, const float* g, float* m, float* v, long n, float
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+      p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale, nullptr, nullptr);
   return check_launch("adam_step");
+}
+
+int fpb200_adam_step_graphable(float* p, const float* g, float* m, float* v, long n, float lr,
+                               float beta1, float beta2, float eps, int* step_state,
+                               float grad_scale, void* stream) {
+  if (n <= 0 || step_state == nullptr) return FPB200_ERR_SHAPE;
+  adam_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, grad_scale, step_state,
+      reinterpret_cast<unsigned int*>(step_state + 1));
+  return check_launch("adam_step_graphable");
 }
 
 }  // extern "C"

@@ -86,6 +86,9 @@ class PackedWeights:
         self._fprop: Dict[str, Tuple[int, torch.Tensor]] = {}
         self._dgrad: Dict[str, Tuple[int, torch.Tensor]] = {}
         self.generation = 0
+        # when True every lookup re-packs into the SAME buffer (CUDA-graph capture: the replayed
+        # graph must contain the repack kernels because the optimiser changes the masters)
+        self.always_repack = False
 
     def invalidate(self) -> None:
         """For updates torch cannot see (raw-pointer kernels such as the fused Adam)."""
@@ -97,7 +100,7 @@ class PackedWeights:
     def fprop(self, name: str, w: torch.Tensor, cin_pad: int) -> torch.Tensor:
         key = self._key(w)
         hit = self._fprop.get(name)
-        if hit is None or hit[0] != key:
+        if hit is None or hit[0] != key or self.always_repack:
             buf = hit[1] if hit is not None and hit[1].device == w.device else None
             self._fprop[name] = (key, ops.repack_fprop(w, cin_pad, buf))
         return self._fprop[name][1]
@@ -105,7 +108,7 @@ class PackedWeights:
     def dgrad(self, name: str, w: torch.Tensor) -> torch.Tensor:
         key = self._key(w)
         hit = self._dgrad.get(name)
-        if hit is None or hit[0] != key:
+        if hit is None or hit[0] != key or self.always_repack:
             buf = hit[1] if hit is not None and hit[1].device == w.device else None
             self._dgrad[name] = (key, ops.repack_dgrad(w, buf))
         return self._dgrad[name][1]

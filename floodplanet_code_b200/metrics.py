@@ -30,10 +30,14 @@ class MicroSegmentationMetrics:
 
     # -- accumulation ------------------------------------------------------------------------
     def reset(self) -> None:
-        self._conf = None
+        if self._conf is not None:
+            self._conf.zero_()
 
     def update_from_confusion(self, conf: torch.Tensor) -> None:
-        self._conf = conf.clone() if self._conf is None else self._conf + conf
+        # in-place on a persistent device tensor: safe to capture in / replay from a CUDA graph
+        if self._conf is None or self._conf.device != conf.device:
+            self._conf = torch.zeros_like(conf)
+        self._conf.add_(conf)
 
     def confusion(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """Confusion counts from flat predictions/targets (host-side convenience, not the hot

@@ -299,6 +299,14 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0) -> None:
     capi.check(st, "adam_step", n=p.numel())
 
 
+def adam_step_graphable(p, g, m, v, lr, beta1, beta2, eps, step_state, grad_scale=1.0) -> None:
+    """Adam with the step counter on the device (int32[2]); CUDA-graph replayable."""
+    st = _lib().fpb200_adam_step_graphable(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                           p.numel(), lr, beta1, beta2, eps, step_state.data_ptr(),
+                                           grad_scale, _stream())
+    capi.check(st, "adam_step_graphable", n=p.numel())
+
+
 # ------------------------------------------------------------------------------------------
 def ingest_scene_tiles(scene: torch.Tensor, tiles: torch.Tensor, th: int, tw: int, c_pad: int) -> torch.Tensor:
     """scene [C,H,W] fp32 (device) + tiles int32 [n,4] (device: h0,w0,valid_h,valid_w) -> NHWC bf16."""

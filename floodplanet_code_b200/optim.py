@@ -40,6 +40,9 @@ class FusedAdam:
                 p.data = view
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
+        # [completed steps, ticket]: the step counter lives on the device so that step() can be
+        # captured once and replayed from a CUDA graph
+        self.step_state = torch.zeros(2, dtype=torch.int32, device=dev)
         self._first_name = next(iter(self.layout))  # slab offset 0
 
     def zero_grad(self, set_to_none: bool = True) -> None:
@@ -69,10 +72,11 @@ class FusedAdam:
         self.unet._engine.packed.invalidate()  # raw-pointer update: bf16 operand copies are stale
         slab = self._grad_slab()
         if slab is not None:
-            ops.adam_step(self.flat, slab, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2, self.eps,
-                          self.step_count, grad_scale)
+            ops.adam_step_graphable(self.flat, slab, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2,
+                                    self.eps, self.step_state, grad_scale)
             self.launches = 1
             return
+        self.step_count = int(self.step_state[0].item()) + 1
         # gradients came from somewhere else (e.g. accumulated): per-tensor launches
         params = dict(self.unet.named_parameters())
         n = 0
@@ -84,4 +88,5 @@ class FusedAdam:
                           self.exp_avg_sq[off:off + nel], self.lr, b1, b2, self.eps, self.step_count,
                           grad_scale)
             n += 1
+        self.step_state[0] += 1
         self.launches = n

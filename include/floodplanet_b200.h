@@ -226,6 +226,13 @@ int fpb200_canvas_to_mask_u8(const float* canvas, const float* weight, uint8_t* 
 int fpb200_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                      float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* Same update with the step counter resident on the device (step_state: int32[2] = {completed
+ * steps, internal ticket}, zero-initialised by the caller); the kernel derives the bias
+ * corrections from it and increments it, so the launch can be replayed from a CUDA graph. */
+int fpb200_adam_step_graphable(float* p, const float* g, float* m, float* v, long n, float lr,
+                               float beta1, float beta2, float eps, int* step_state,
+                               float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

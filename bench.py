@@ -296,12 +296,22 @@ def run_ours(args):
     conv_ms = sum(d["ms"] for d in fam.values())
     conv_flops = sum(d["flops"] for d in fam.values())
     dom = max(fam.items(), key=lambda kv: kv[1]["ms"])[0] if fam else None
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "r01_traffic.json"
+    if tp.exists() and dom is not None:
+        tj = json.loads(tp.read_text())
+        key = "conv3x3_wgrad_kernel_all" if dom == "wgrad" else "conv3x3_halo_kernel_all"
+        traffic = tj[key]["dram_bytes_per_launch"]
+        traffic_src = ("mean dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel over one "
+                       "training step at batch 64 (profiles/r01_traffic.json, ncu)")
     roofline = None
     if dom is not None:
         kname = {"fprop": "conv3x3_igemm_kernel (fprop launches)", "dgrad": "conv3x3_igemm_kernel (dgrad launches)",
                  "wgrad": "conv3x3_wgrad_kernel (+split-K reduce)"}[dom]
         roofline = {"bound": "tensor", "kernel": kname, "achieved": roof_all[dom]["achieved"], "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": roof_all[dom]["frac"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": roof_all[dom]["frac"], "traffic": traffic,
+                    "traffic_source": traffic_src,
+                    "algorithmic_flops_per_launch": fam[dom]["flops"] / fam[dom]["launches"],
                     "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                     "share_of_step": roof_all[dom]["ms_per_step"] / instrumented_ms_per_step,
                     "timed_with": ("events around every conv launch, eager instrumented pass of the same "

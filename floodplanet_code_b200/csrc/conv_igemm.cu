@@ -20,10 +20,15 @@
 // 1.27 (halo overhead) and every weight tile [BN x KCH] is used by two MMA tiles, which is
 // what lifts the kernel from smem-fill bound to tensor-pipe bound.
 //
+// Items are ordered patch-major / channel-block-minor: with 148 CTAs and 1, 2 or 4 channel blocks
+// every CTA keeps one channel block for the whole launch (its BatchNorm partials stay in
+// registers) while neighbouring CTAs work on the same patch, so the activation box is fetched
+// from HBM once and re-served from L2 for the other channel blocks.
+//
 // Pipeline: persistent CTAs (one per SM), warp specialised
 //   warp 0    TMA producer: ring A (activation boxes), ring B (weight tiles per tap)
 //   warp 1    tcgen05.mma issuer + TMEM allocator
-//   warps 2-5 epilogue: tcgen05.ld -> registers -> fused epilogue -> global
+//   warps 2.. epilogue (4, or 8 for BN = 64): tcgen05.ld -> registers -> fused epilogue -> global
 // TMEM holds 2 (double buffer) x 2 (tiles) x BN fp32 accumulator columns, so the epilogue
 // of one patch overlaps the MMAs of the next.
 //
@@ -58,13 +63,12 @@ struct HaloParams {
   const float* scale;
   const float* shift;
   int relu;
-  float* stat_partials;  // [gridDim.x*4][2][Cout]
+  float* stat_partials;  // [fpb200_conv_stat_rows()][2][Cout], row = CTA * epilogue warps + warp
 };
 
 constexpr int kPatch = 16;        // patch edge in pixels
 constexpr int kBox = kPatch + 2;  // with halo
 constexpr int kBoxRows = kBox * kBox;
-constexpr int kHaloThreads = 192;
 
 template <int BN, int KCH>
 struct HaloCfg {
@@ -73,7 +77,11 @@ struct HaloCfg {
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;    // ring pitch
   static constexpr int kBBytes = BN * kRowBytes;
   static constexpr int kNB = BN >= 128 ? 6 : 8;                    // weight ring depth
-  static constexpr int kStageOut = 4 * 2 * 4096;                   // epilogue staging: 2 x 4 KB per warp
+  // epilogue warps: one per (TMEM lane quadrant, MMA tile) when the MMAs are short (BN = 64:
+  // 32 tensor cycles each, the epilogue is co-critical), one per quadrant otherwise
+  static constexpr int kEpiWarps = BN >= 128 ? 4 : 8;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kStageOut = kEpiWarps * 2 * 4096;           // epilogue staging: 2 x 4 KB per warp
   static constexpr int kBudget = 212 * 1024;
   static constexpr int kNARaw = (kBudget - kStageOut - kNB * kBBytes) / kASlot;
   static constexpr int kNA = kNARaw > 4 ? 4 : kNARaw;
@@ -86,7 +94,7 @@ struct HaloCfg {
 };
 
 template <int BN, int KCH>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(HaloCfg<BN, KCH>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
   using Cfg = HaloCfg<BN, KCH>;
@@ -123,12 +131,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmY);
     for (int s = 0; s < kNA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < kNB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), Cfg::kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   if (p.scale != nullptr) {
-    for (int c = threadIdx.x; c < p.Cout; c += kHaloThreads) {
+    for (int c = threadIdx.x; c < p.Cout; c += Cfg::kThreads) {
       s_scale[c] = p.scale[c];
       s_shift[c] = p.shift[c];
     }
@@ -145,8 +153,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int n_blk = item / p.num_patches;
-        const int patch = item - n_blk * p.num_patches;
+        const int patch = item / p.num_n_blks;   // n_blk-minor: CTAs b, b+1 share a patch (L2 hit)
+        const int n_blk = item - patch * p.num_n_blks;
         const int pw = patch % p.patches_w;
         const int t2 = patch / p.patches_w;
         const int ph = t2 % p.patches_h;
@@ -224,6 +232,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // MMA tile row = (th, tw) = (row >> 3, row & 7)
     const int ew = warp - 2;
+    constexpr int kTilesPerWarp = Cfg::kEpiWarps == 8 ? 1 : 2;
+    const int t_first = Cfg::kEpiWarps == 8 ? (ew >> 2) : 0;   // 8 warps: warps 2-5 tile 0, 6-9 tile 1
     const bool do_stats = p.stat_partials != nullptr;
     const bool do_affine = p.scale != nullptr;
     const uint32_t stg0 = stg_base + ew * 8192;   // two 4 KB staging tiles, used alternately
@@ -235,19 +245,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int cur_n_blk = -1;
     auto flush_stats = [&]() {
       if (do_stats && cur_n_blk >= 0) {
-        float* dst = p.stat_partials + (size_t)(blockIdx.x * 4 + ew) * 2 * p.Cout + cur_n_blk * BN;
+        float* dst = p.stat_partials + (size_t)(blockIdx.x * Cfg::kEpiWarps + ew) * 2 * p.Cout + cur_n_blk * BN;
 #pragma unroll
         for (int u = 0; u < kUnits; ++u) {
-          *reinterpret_cast<float2*>(dst + u * 64 + 2 * lane) = make_float2(acc_sum[u][0], acc_sum[u][1]);
-          *reinterpret_cast<float2*>(dst + p.Cout + u * 64 + 2 * lane) = make_float2(acc_sq[u][0], acc_sq[u][1]);
+          // this (row, column) slot is owned by exactly this thread and was zeroed by the host,
+          // so a CTA that comes back to an n_blk accumulates without atomics
+          float2* d0 = reinterpret_cast<float2*>(dst + u * 64 + 2 * lane);
+          float2* d1 = reinterpret_cast<float2*>(dst + p.Cout + u * 64 + 2 * lane);
+          const float2 o0 = *d0, o1 = *d1;
+          *d0 = make_float2(o0.x + acc_sum[u][0], o0.y + acc_sum[u][1]);
+          *d1 = make_float2(o1.x + acc_sq[u][0], o1.y + acc_sq[u][1]);
           acc_sum[u][0] = acc_sum[u][1] = acc_sq[u][0] = acc_sq[u][1] = 0.f;
         }
       }
     };
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int n_blk = item / p.num_patches;
-      const int patch = item - n_blk * p.num_patches;
+      const int patch = item / p.num_n_blks;
+      const int n_blk = item - patch * p.num_n_blks;
       const int pw = patch % p.patches_w;
       const int t2 = patch / p.patches_w;
       const int ph = t2 % p.patches_h;
@@ -259,7 +274,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const int py = ph * kPatch + (row >> 3);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int tt = 0; tt < kTilesPerWarp; ++tt) {
+        const int t = t_first + tt;
         const int px = pw * kPatch + t * 8 + (row & 7);
         const bool valid = (px < p.W) && (py < p.H);
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
@@ -355,7 +371,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int items = p.num_patches * p.num_n_blks;
   int grid = sm_count();
   if (grid > items) grid = items;
-  kern<<<grid, kHaloThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
   return check_launch("conv3x3_halo");
 }
 
@@ -420,7 +436,7 @@ int fpb200_debug_conv_mode(int impl) {
   return 0;
 }
 
-int fpb200_conv_stat_rows(void) { return 4 * fp::sm_count(); }
+int fpb200_conv_stat_rows(void) { return 8 * fp::sm_count(); }
 
 int fpb200_conv3x3_fprop_bf16_nhwc(const void* x, long ldx, const void* w_packed, void* y, long ldy,
                                    int N, int H, int W, int Cin, int Cout, const float* scale,

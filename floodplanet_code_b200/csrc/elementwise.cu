@@ -234,29 +234,35 @@ __global__ void bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, long l
   }
 }
 
-// BN apply + ReLU fused with MaxPool2d(2).  One thread = one 2x2 window x 8 channels.
-__global__ void bn_apply_relu_maxpool2_kernel(const __nv_bfloat16* __restrict__ y, long ldy,
-                                              __nv_bfloat16* __restrict__ a, long lda,
-                                              __nv_bfloat16* __restrict__ pooled, long ldp,
-                                              uint8_t* __restrict__ pool_idx,
-                                              const float* __restrict__ scale,
-                                              const float* __restrict__ shift, int N, int H, int W,
-                                              int CG) {
+// BN apply + ReLU fused with MaxPool2d(2).  One block = one row of 2x2 windows (n, ho); one
+// thread = one window x 8 channels; 32-bit index math.
+__global__ void __launch_bounds__(256)
+bn_apply_relu_maxpool2_kernel(const __nv_bfloat16* __restrict__ y, long ldy,
+                              __nv_bfloat16* __restrict__ a, long lda,
+                              __nv_bfloat16* __restrict__ pooled, long ldp,
+                              uint8_t* __restrict__ pool_idx, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int H, int W, int CG) {
   const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;  // windows incl. the ragged last row/col
   const int Hp = H >> 1, Wp = W >> 1;
-  const long total = (long)N * Hc * Wc * CG;
+  const int n = blockIdx.x / Hc;
+  const int ho = blockIdx.x - n * Hc;
   const bool affine = scale != nullptr;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const int cg = i % CG;
-    long t = i / CG;
-    const int wo = t % Wc; t /= Wc;
-    const int ho = t % Hc;
-    const int n = t / Hc;
+  const int work = Wc * CG;
+  for (int i = threadIdx.x; i < work; i += blockDim.x) {
+    const int wo = i / CG;
+    const int cg = i - wo * CG;
     float sc[8], sh[8];
     if (affine) {
       load8f(scale + cg * 8, sc);
       load8f(shift + cg * 8, sh);
+    }
+    uint4 in[4];
+    bool ok[4];
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
+      ok[pos] = h < H && w < W;
+      if (ok[pos]) in[pos] = ld_stream(y + (((long)n * H + h) * W + w) * ldy + cg * 8);
     }
     float best[8];
     int bidx[8];
@@ -264,17 +270,17 @@ __global__ void bn_apply_relu_maxpool2_kernel(const __nv_bfloat16* __restrict__ 
     for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bidx[j] = 0; }
 #pragma unroll
     for (int pos = 0; pos < 4; ++pos) {
-      const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
-      if (h < H && w < W) {
-        const long px = ((long)n * H + h) * W + w;
+      if (ok[pos]) {
+        const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
         float f[8];
-        unpack8(ld_stream(y + px * ldy + cg * 8), f);
+        unpack8(in[pos], f);
         if (affine) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
           // round through bf16 so the pooled value equals the stored activation bit for bit
           const uint4 packed = pack8(f);
-          if (a != nullptr) *reinterpret_cast<uint4*>(a + px * lda + cg * 8) = packed;
+          if (a != nullptr)
+            *reinterpret_cast<uint4*>(a + (((long)n * H + h) * W + w) * lda + cg * 8) = packed;
           unpack8(packed, f);
         }
 #pragma unroll
@@ -294,24 +300,23 @@ __global__ void bn_apply_relu_maxpool2_kernel(const __nv_bfloat16* __restrict__ 
   }
 }
 
-__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dpooled, long lddp,
-                                    const uint8_t* __restrict__ pool_idx,
-                                    const __nv_bfloat16* __restrict__ dskip, long ldds,
-                                    __nv_bfloat16* __restrict__ dx, long lddx, int N, int H, int W,
-                                    int CG) {
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dpooled, long lddp,
+                    const uint8_t* __restrict__ pool_idx, const __nv_bfloat16* __restrict__ dskip,
+                    long ldds, __nv_bfloat16* __restrict__ dx, long lddx, int H, int W, int CG) {
   const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
   const int Hp = H >> 1, Wp = W >> 1;
-  const long total = (long)N * Hc * Wc * CG;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const int cg = i % CG;
-    long t = i / CG;
-    const int wo = t % Wc; t /= Wc;
-    const int ho = t % Hc;
-    const int n = t / Hc;
+  const int n = blockIdx.x / Hc;
+  const int ho = blockIdx.x - n * Hc;
+  const int work = Wc * CG;
+  for (int i = threadIdx.x; i < work; i += blockDim.x) {
+    const int wo = i / CG;
+    const int cg = i - wo * CG;
     const bool has_pool = ho < Hp && wo < Wp;
     float g[8];
     uint2 ib = make_uint2(0, 0);
+    uint4 sk[4];
+    bool ok[4];
     if (has_pool) {
       const long pp = ((long)n * Hp + ho) * Wp + wo;
       unpack8(ld_stream(dpooled + pp * lddp + cg * 8), g);
@@ -320,11 +325,17 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dpooled, l
 #pragma unroll
     for (int pos = 0; pos < 4; ++pos) {
       const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
-      if (h < H && w < W) {
-        const long px = ((long)n * H + h) * W + w;
+      ok[pos] = h < H && w < W;
+      if (ok[pos] && dskip != nullptr)
+        sk[pos] = ld_stream(dskip + (((long)n * H + h) * W + w) * ldds + cg * 8);
+    }
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      if (ok[pos]) {
+        const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
         float f[8];
         if (dskip != nullptr) {
-          unpack8(ld_stream(dskip + px * ldds + cg * 8), f);
+          unpack8(sk[pos], f);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = 0.f;
@@ -337,7 +348,7 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dpooled, l
             if (sel == pos) f[j] += g[j];
           }
         }
-        *reinterpret_cast<uint4*>(dx + px * lddx + cg * 8) = pack8(f);
+        *reinterpret_cast<uint4*>(dx + (((long)n * H + h) * W + w) * lddx + cg * 8) = pack8(f);
       }
     }
   }
@@ -722,20 +733,18 @@ int fpb200_bn_apply_relu_maxpool2(const void* y, long ldy, void* a, long lda, vo
                                   long ldp, uint8_t* pool_idx, const float* scale,
                                   const float* shift, int N, int H, int W, int C, void* stream) {
   if (C % 8 != 0 || ldy % 8 != 0 || ldp % 8 != 0 || (a && lda % 8 != 0)) return FPB200_ERR_SHAPE;
-  const long total = (long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  bn_apply_relu_maxpool2_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+  bn_apply_relu_maxpool2_kernel<<<N * ((H + 1) / 2), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y, ldy, (__nv_bfloat16*)a, lda, (__nv_bfloat16*)pooled, ldp, pool_idx,
-      scale, shift, N, H, W, C / 8);
+      scale, shift, H, W, C / 8);
   return check_launch("bn_apply_relu_maxpool2");
 }
 
 int fpb200_maxpool2_bwd(const void* dpooled, long lddp, const uint8_t* pool_idx, const void* dskip,
                         long ldds, void* dx, long lddx, int N, int H, int W, int C, void* stream) {
   if (C % 8 != 0 || lddp % 8 != 0 || lddx % 8 != 0) return FPB200_ERR_SHAPE;
-  const long total = (long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  maxpool2_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+  maxpool2_bwd_kernel<<<N * ((H + 1) / 2), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dpooled, lddp, pool_idx, (const __nv_bfloat16*)dskip, ldds,
-      (__nv_bfloat16*)dx, lddx, N, H, W, C / 8);
+      (__nv_bfloat16*)dx, lddx, H, W, C / 8);
   return check_launch("maxpool2_bwd");
 }
 

@@ -76,12 +76,13 @@ struct HaloCfg {
   static constexpr int kABytes = kBoxRows * kRowBytes;             // bytes the TMA writes
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;    // ring pitch
   static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kNB = BN >= 128 ? 6 : 8;                    // weight ring depth
+  static constexpr int kNB = BN >= 128 ? 6 : 12;                   // weight ring depth (<= 16)
   // epilogue warps: one per (TMEM lane quadrant, MMA tile) when the MMAs are short (BN = 64:
   // 32 tensor cycles each, the epilogue is co-critical), one per quadrant otherwise
   static constexpr int kEpiWarps = BN >= 128 ? 4 : 8;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kStageOut = kEpiWarps * 2 * 4096;           // epilogue staging: 2 x 4 KB per warp
+  static constexpr int kStgBufs = BN >= 128 ? 2 : 1;               // staging tiles per epilogue warp
+  static constexpr int kStageOut = kEpiWarps * kStgBufs * 4096;    // epilogue staging, 4 KB tiles
   static constexpr int kBudget = 212 * 1024;
   static constexpr int kNARaw = (kBudget - kStageOut - kNB * kBBytes) / kASlot;
   static constexpr int kNA = kNARaw > 4 ? 4 : kNARaw;
@@ -112,11 +113,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t bar_base = smem_base + Cfg::kDataBytes;
   auto afull = [&](int s) { return bar_base + 8u * s; };            // 4
   auto aempty = [&](int s) { return bar_base + 32u + 8u * s; };     // 4
-  auto bfull = [&](int s) { return bar_base + 64u + 8u * s; };      // 8
-  auto bempty = [&](int s) { return bar_base + 128u + 8u * s; };    // 8
-  auto tfull = [&](int s) { return bar_base + 192u + 8u * s; };     // 2
-  auto tempty = [&](int s) { return bar_base + 208u + 8u * s; };    // 2
-  const uint32_t tmem_slot = bar_base + 224u;
+  auto bfull = [&](int s) { return bar_base + 64u + 8u * s; };      // 16
+  auto bempty = [&](int s) { return bar_base + 192u + 8u * s; };    // 16
+  auto tfull = [&](int s) { return bar_base + 320u + 8u * s; };     // 2
+  auto tempty = [&](int s) { return bar_base + 336u + 8u * s; };    // 2
+  const uint32_t tmem_slot = bar_base + 352u;
   float* s_scale = reinterpret_cast<float*>(smem_al + Cfg::kDataBytes + 512);
   float* s_shift = s_scale + 512;
 
@@ -145,7 +146,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base =
-      *reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::kDataBytes + 224);
+      *reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::kDataBytes + 352);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -236,7 +237,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int t_first = Cfg::kEpiWarps == 8 ? (ew >> 2) : 0;   // 8 warps: warps 2-5 tile 0, 6-9 tile 1
     const bool do_stats = p.stat_partials != nullptr;
     const bool do_affine = p.scale != nullptr;
-    const uint32_t stg0 = stg_base + ew * 8192;   // two 4 KB staging tiles, used alternately
+    const uint32_t stg0 = stg_base + ew * (Cfg::kStgBufs * 4096);   // this warp's staging tile(s)
     uint32_t stg_sel = 0;
     constexpr int kUnits = BN / 64;
     float acc_sum[kUnits][2], acc_sq[kUnits][2];
@@ -284,8 +285,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // the TMA store issued two units ago must have finished reading this staging tile
           const uint32_t stg = stg0 + stg_sel * 4096;
           const uint32_t stg_row = stg + lane * 128;
-          stg_sel ^= 1u;
-          if (lane == 0) tma_store_wait_read_keep1();
+          if (Cfg::kStgBufs == 2) {
+            stg_sel ^= 1u;
+            if (lane == 0) tma_store_wait_read_keep1();
+          } else {
+            if (lane == 0) tma_store_wait_read();
+          }
           __syncwarp();
 #pragma unroll
           for (int hlf = 0; hlf < 2; ++hlf) {

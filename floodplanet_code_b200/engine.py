@@ -155,6 +155,11 @@ class UNetEngine:
         self.grad_done_hook: Optional[Callable[[torch.Tensor, int], None]] = None
         # optional profiler: when a list, (tag, flops, start_event, end_event) per conv launch
         self.conv_events: Optional[list] = None
+        # backward: run every wgrad on a second stream.  wgrad is off the critical path (only the
+        # optimiser needs dW) and tensor-bound, so it overlaps the HBM-bound BatchNorm-backward
+        # passes of the next layer, which run on the leftover warps/registers of the same SMs.
+        self.overlap_wgrad = True
+        self._side_stream: Optional[torch.cuda.Stream] = None
         self.launches = 0  # kernels launched by the last forward/backward (for bench accounting)
 
     # -------------------------------------------------------------------------------------
@@ -324,13 +329,26 @@ class UNetEngine:
         grads = {k: slab[o:o + nel].view(params[k].shape) for k, (o, nel) in layout.items()}
         launches = 1
         ready_upto = 0
+        main = torch.cuda.current_stream(dev)
+        side = None
+        if self.overlap_wgrad and self.conv_events is None:
+            if self._side_stream is None or self._side_stream.device != dev:
+                self._side_stream = torch.cuda.Stream(device=dev)
+            side = self._side_stream
+        # one split-K workspace for all layers (the wgrads are serialised on one stream)
+        ws_need = max(ops.wgrad_workspace_bytes(n, sizes[sp.level][0], sizes[sp.level][1],
+                                                self._cin_pad_of(j), sp.cout)
+                      for j, sp in enumerate(self.specs)) // 4
+        ws = torch.empty(ws_need, **f32)
 
         def mark_ready(name_last: str):
-            """All grads from slab[ready_upto] through `name_last` are final."""
+            """All grads from slab[ready_upto] through `name_last` are final (enqueued)."""
             nonlocal ready_upto
             o, nel = layout[name_last]
             end = (o + nel + 3) // 4 * 4
             if self.grad_ready_hook is not None and end > ready_upto:
+                if side is not None:
+                    main.wait_stream(side)   # weight grads of this bucket come from the side stream
                 self.grad_ready_hook(slab, ready_upto, end)
             ready_upto = end
 
@@ -346,7 +364,6 @@ class UNetEngine:
         mark_ready("outc.conv.weight")
 
         bn_rows = ops.bn_bwd_rows()
-        ws_cache: Dict[int, torch.Tensor] = {}
 
         def layer_backward(i: int, da: torch.Tensor, need_dx: bool,
                            dx_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
@@ -361,14 +378,14 @@ class UNetEngine:
                                 grads[f"{s.bn}.weight"], grads[f"{s.bn}.bias"], coef)
             dy = torch.empty((n, hh, ww, s.cout), **bf)
             ops.bn_relu_bwd_apply(da, sv.y, dy, sv.scale, sv.shift, coef)
-            cin_pad = self._cin_pad_of(i)
-            need = ops.wgrad_workspace_bytes(n, hh, ww, cin_pad, s.cout) // 4
-            ws = ws_cache.get(0)
-            if ws is None or ws.numel() < need:
-                ws = torch.empty(need, **f32)
-                ws_cache[0] = ws
-            self._timed("wgrad", i, n, hh * ww,
-                        lambda: ops.conv3x3_wgrad(sv.x, dy, grads[f"{s.conv}.weight"], ws, s.cin))
+            if side is not None:
+                side.wait_stream(main)                      # dy is ready
+                with torch.cuda.stream(side):
+                    ops.conv3x3_wgrad(sv.x, dy, grads[f"{s.conv}.weight"], ws, s.cin)
+                dy.record_stream(side)                      # keep dy alive until the side stream is done
+            else:
+                self._timed("wgrad", i, n, hh * ww,
+                            lambda: ops.conv3x3_wgrad(sv.x, dy, grads[f"{s.conv}.weight"], ws, s.cin))
             launches += 5
             dx = None
             if need_dx:
@@ -406,6 +423,9 @@ class UNetEngine:
             d_mid = layer_backward(li, d_skip, True); li -= 1
             d_pool = layer_backward(li, d_mid, lvl > 0); li -= 1
         assert li == -1
+        if side is not None:
+            main.wait_stream(side)
+            ws.record_stream(side)
         mark_ready(self.names[0])
         if self.grad_done_hook is not None:
             self.grad_done_hook(slab, total)

@@ -399,3 +399,31 @@ def test_adam_matches_torch(ops):
         opt.step()
         ops.adam_step(p, gr, m, v, 1e-4, 0.9, 0.999, 1e-8, step)
     assert rel(p, pr.detach()) < 1e-6
+
+
+def test_bn_fold_eval_and_eval_conv_epilogue(ops):
+    """eval-mode BatchNorm (+ conv bias) folded into the conv epilogue == F.batch_norm(training=False)."""
+    n, h, w, cin, c = 2, 20, 24, 64, 128
+    x = rand_act(n, h, w, cin, 30)
+    wt = rand_w(c, cin, 31)
+    g = torch.Generator(device="cuda").manual_seed(32)
+    gamma = torch.rand(c, generator=g, device="cuda") + 0.5
+    beta = torch.randn(c, generator=g, device="cuda") * 0.1
+    bias = torch.randn(c, generator=g, device="cuda") * 0.1
+    rm = torch.randn(c, generator=g, device="cuda") * 0.2
+    rv = torch.rand(c, generator=g, device="cuda") + 0.5
+    scale, shift = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    ops.bn_fold_eval(gamma, beta, bias, rm, rv, 1e-5, scale, shift)
+    a = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3_fprop(x, ops.repack_fprop(wt, cin), a, scale=scale, shift=shift, relu=True)
+    ref = F.relu(F.batch_norm(F.conv2d(nchw(x.float()), wt, bias, padding=1), rm, rv, gamma, beta, False, 0.1, 1e-5))
+    assert rel(nchw(a.float()), ref) < 1e-2
+
+
+def test_error_status_raises_runtime_error(ops):
+    x = rand_act(1, 16, 16, 24, 33)          # 24 input channels: not a supported padding
+    y = torch.empty(1, 16, 16, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError, match="conv3x3_fprop"):
+        ops.conv3x3_fprop(x, torch.empty(64, 9, 24, dtype=torch.bfloat16, device="cuda"), y)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.ingest([torch.zeros(1, 4, 16, 16)], 16)

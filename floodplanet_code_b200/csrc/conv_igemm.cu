@@ -50,7 +50,6 @@ int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, lon
                      float* stat_partials, cudaStream_t stream);
 }
 
-static int g_conv_impl = 2;     // bring-up switch (debug hook below): 1 = per-tap kernel
 
 struct HaloParams {
   int N, H, W;
@@ -383,9 +382,6 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, long ldy, int N,
                             int H, int W, int Cin, int Cout, const float* scale, const float* shift,
                             int relu, float* stat_partials, cudaStream_t stream) {
-  if (g_conv_impl == 1)
-    return v1::conv3x3_dispatch(x, ldx, w_packed, y, ldy, N, H, W, Cin, Cout, scale, shift, relu,
-                                stat_partials, stream);
   if (N <= 0 || H <= 0 || W <= 0) return FPB200_ERR_SHAPE;
   if (Cin % 16 != 0 || Cout % 64 != 0 || Cout > 2048) return FPB200_ERR_SHAPE;
   if ((ldx % 8) != 0 || (ldy % 8) != 0 || ldx < Cin || ldy < Cout) return FPB200_ERR_SHAPE;
@@ -435,10 +431,12 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
 
 extern "C" {
 
-// bring-up hook (not part of the public header): choose the conv implementation under test
-int fpb200_debug_conv_mode(int impl) {
-  fp::g_conv_impl = impl;
-  return 0;
+int fpb200_conv3x3_pertap_bf16_nhwc(const void* x, long ldx, const void* w_packed, void* y, long ldy,
+                                    int N, int H, int W, int Cin, int Cout, const float* scale,
+                                    const float* shift, int relu, float* stat_partials,
+                                    void* stream) {
+  return fp::v1::conv3x3_dispatch(x, ldx, w_packed, y, ldy, N, H, W, Cin, Cout, scale, shift, relu,
+                                  stat_partials, static_cast<cudaStream_t>(stream));
 }
 
 int fpb200_conv_stat_rows(void) { return 8 * fp::sm_count(); }

@@ -24,12 +24,8 @@ def ops():
 @pytest.fixture(params=["halo", "per_tap"])
 def conv_impl(request):
     """Both conv generations stay under test: the halo kernel (product path) and the
-    first-generation one-box-per-tap kernel it was validated against."""
-    from floodplanet_code_b200 import capi
-    lib = capi.load()
-    lib.fpb200_debug_conv_mode({"halo": 2, "per_tap": 1}[request.param])
-    yield request.param
-    lib.fpb200_debug_conv_mode(2)
+    first-generation one-box-per-tap kernel kept in the library as its cross-check."""
+    return request.param == "per_tap"
 
 
 def rel(a, b):
@@ -78,7 +74,7 @@ def test_conv3x3_fprop_and_stats(ops, conv_impl, n, h, w, cin, cout):
     wp = ops.repack_fprop(wt, cin)
     y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
     parts = torch.empty(ops.stat_rows(), 2, cout, dtype=torch.float32, device="cuda")
-    ops.conv3x3_fprop(x, wp, y, stat_partials=parts)
+    ops.conv3x3_fprop(x, wp, y, stat_partials=parts, per_tap_kernel=conv_impl)
     torch.cuda.synchronize()
     ref = F.conv2d(nchw(x.float()), wt, padding=1)
     err = rel(nchw(y.float()), ref)
@@ -99,7 +95,7 @@ def test_conv3x3_fprop_affine_relu_into_concat_view(ops, conv_impl, n, h, w, cin
     scale = torch.rand(cout, generator=g, device="cuda") + 0.5
     shift = torch.randn(cout, generator=g, device="cuda") * 0.2
     buf = torch.full((n, h, w, 2 * cout), 7.0, dtype=torch.bfloat16, device="cuda")
-    ops.conv3x3_fprop(x, wp, buf[..., :cout], scale=scale, shift=shift, relu=True)
+    ops.conv3x3_fprop(x, wp, buf[..., :cout], scale=scale, shift=shift, relu=True, per_tap_kernel=conv_impl)
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(nchw(x.float()), wt, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
     assert rel(nchw(buf[..., :cout].float()), ref) < 1e-2
@@ -108,7 +104,7 @@ def test_conv3x3_fprop_affine_relu_into_concat_view(ops, conv_impl, n, h, w, cin
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (1, 20, 24, 128, 256), (1, 19, 19, 256, 64),
                                             (1, 16, 16, 1024, 512)])
-def test_conv3x3_dgrad(ops, conv_impl, n, h, w, cin, cout):
+def test_conv3x3_dgrad(ops, n, h, w, cin, cout):
     dy = rand_act(n, h, w, cout, 6)
     wt = rand_w(cout, cin, 7)
     wd = ops.repack_dgrad(wt)

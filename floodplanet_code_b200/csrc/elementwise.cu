@@ -378,15 +378,36 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, long ldda,
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  for (long px = (long)blockIdx.x * TP + pl; px < num_pixels; px += (long)gridDim.x * TP) {
+  // two pixels per iteration: four independent 16-byte loads in flight per thread
+  const long pstride = (long)gridDim.x * TP;
+  for (long px = (long)blockIdx.x * TP + pl; px < num_pixels; px += 2 * pstride) {
+    const long px2 = px + pstride;
+    const bool has2 = px2 < num_pixels;
+    const uint4 g0 = ld_stream(da + px * ldda + cg * 8);
+    const uint4 v0 = ld_stream(y + px * ldy + cg * 8);
+    uint4 g1 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+    if (has2) {
+      g1 = ld_stream(da + px2 * ldda + cg * 8);
+      v1 = ld_stream(y + px2 * ldy + cg * 8);
+    }
     float g[8], v[8];
-    unpack8(ld_stream(da + px * ldda + cg * 8), g);
-    unpack8(ld_stream(y + px * ldy + cg * 8), v);
+    unpack8(g0, g);
+    unpack8(v0, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
       s1[j] += gg;
       s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
+    }
+    if (has2) {
+      unpack8(g1, g);
+      unpack8(v1, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+        s1[j] += gg;
+        s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
+      }
     }
   }
 #pragma unroll

@@ -1,11 +1,6 @@
+# Full GPU validation: tests, smoke, default bench, reference arm (what the driver runs at round end)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu --tb=short -p no:cacheprovider -x > gpurun_out/t_all.log 2>&1; echo "== gpu tests exit $?"; tail -n 8 gpurun_out/t_all.log
-timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "== smoke exit $?"; tail -n 2 gpurun_out/smoke.log
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_full.log 2>&1; echo "== bench exit $?"; python - <<'PY'
-import json
-l=[x for x in open('gpurun_out/bench_full.log') if x.startswith('{')]
-if l:
-    d=json.loads(l[-1]); r=d['roofline']
-    print('value',round(d['value'],1),'ms',round(d['ms_per_step'],2),'e2e',round(d['e2e']['value'],1),'clocks',d['clocks'])
-    print('families',{k:(round(v['achieved']),round(v['ms_per_step'],2)) for k,v in r['families'].items()},'conv share',round(r['all_conv']['share_of_step'],3))
-PY
+timeout 900 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "== gpu tests exit $?"; tail -n 3 gpurun_out/t_all.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "== smoke exit $?"; tail -n 1 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "== bench exit $?"; tail -n 1 gpurun_out/bench_default.log | cut -c1-600
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "== ref arm exit $?"; tail -n 1 gpurun_out/bench_ref.log | cut -c1-300

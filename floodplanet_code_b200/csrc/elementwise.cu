@@ -378,36 +378,15 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, long ldda,
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  // two pixels per iteration: four independent 16-byte loads in flight per thread
-  const long pstride = (long)gridDim.x * TP;
-  for (long px = (long)blockIdx.x * TP + pl; px < num_pixels; px += 2 * pstride) {
-    const long px2 = px + pstride;
-    const bool has2 = px2 < num_pixels;
-    const uint4 g0 = ld_stream(da + px * ldda + cg * 8);
-    const uint4 v0 = ld_stream(y + px * ldy + cg * 8);
-    uint4 g1 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
-    if (has2) {
-      g1 = ld_stream(da + px2 * ldda + cg * 8);
-      v1 = ld_stream(y + px2 * ldy + cg * 8);
-    }
+  for (long px = (long)blockIdx.x * TP + pl; px < num_pixels; px += (long)gridDim.x * TP) {
     float g[8], v[8];
-    unpack8(g0, g);
-    unpack8(v0, v);
+    unpack8(ld_stream(da + px * ldda + cg * 8), g);
+    unpack8(ld_stream(y + px * ldy + cg * 8), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
       s1[j] += gg;
       s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
-    }
-    if (has2) {
-      unpack8(g1, g);
-      unpack8(v1, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-        s1[j] += gg;
-        s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
-      }
     }
   }
 #pragma unroll
@@ -511,46 +490,54 @@ __device__ __forceinline__ void bilinear_src(int dst, float ratio, int in_size, 
   l0 = 1.f - l1;
 }
 
-// One block per output row (n, ho): the vertical taps / weights are block-uniform, indices are
-// 32-bit, and consecutive threads write consecutive 16-byte channel groups of the row.
+// One block per group of kUpRows output rows of one image: the vertical taps / weights are
+// block-uniform, each thread keeps its horizontal taps / weights for all rows of the group,
+// indices are 32-bit, and consecutive threads write consecutive 16-byte channel groups.
+constexpr int kUpRows = 4;
+
 __global__ void __launch_bounds__(256)
 upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
                           __nv_bfloat16* __restrict__ out, long ldo, int h, int w, int Ho, int Wo,
                           int CG, int pad_top, int pad_left, float rh, float rw) {
-  const int row = blockIdx.x;
-  const int n = row / Ho;
-  const int ho = row - n * Ho;
-  const int uh = ho - pad_top;
-  const bool row_in = uh >= 0 && uh < 2 * h;
-  int h0 = 0, h1 = 0;
-  float lh0 = 0.f, lh1 = 0.f;
-  if (row_in) bilinear_src(uh, rh, h, h0, h1, lh0, lh1);
-  const __nv_bfloat16* r0 = x + ((long)n * h + h0) * w * ldx;
-  const __nv_bfloat16* r1 = x + ((long)n * h + h1) * w * ldx;
-  __nv_bfloat16* orow = out + (long)row * Wo * ldo;
+  const int groups = (Ho + kUpRows - 1) / kUpRows;
+  const int n = blockIdx.x / groups;
+  const int ho0 = (blockIdx.x - n * groups) * kUpRows;
+  const __nv_bfloat16* xin = x + (long)n * h * w * ldx;
   const int work = Wo * CG;
   for (int i = threadIdx.x; i < work; i += blockDim.x) {
     const int wo = i / CG;
     const int cg = i - wo * CG;
     const int uw = wo - pad_left;
-    float o[8];
-    if (row_in && uw >= 0 && uw < 2 * w) {
-      int w0, w1;
-      float lw0, lw1;
-      bilinear_src(uw, rw, w, w0, w1, lw0, lw1);
-      float v00[8], v01[8], v10[8], v11[8];
-      unpack8(*reinterpret_cast<const uint4*>(r0 + (long)w0 * ldx + cg * 8), v00);
-      unpack8(*reinterpret_cast<const uint4*>(r0 + (long)w1 * ldx + cg * 8), v01);
-      unpack8(*reinterpret_cast<const uint4*>(r1 + (long)w0 * ldx + cg * 8), v10);
-      unpack8(*reinterpret_cast<const uint4*>(r1 + (long)w1 * ldx + cg * 8), v11);
+    const bool col_in = uw >= 0 && uw < 2 * w;
+    int w0 = 0, w1 = 0;
+    float lw0 = 0.f, lw1 = 0.f;
+    if (col_in) bilinear_src(uw, rw, w, w0, w1, lw0, lw1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = lh0 * (lw0 * v00[j] + lw1 * v01[j]) + lh1 * (lw0 * v10[j] + lw1 * v11[j]);
-    } else {
+    for (int r = 0; r < kUpRows; ++r) {
+      const int ho = ho0 + r;
+      if (ho >= Ho) break;
+      const int uh = ho - pad_top;
+      float o[8];
+      if (col_in && uh >= 0 && uh < 2 * h) {
+        int h0, h1;
+        float lh0, lh1;
+        bilinear_src(uh, rh, h, h0, h1, lh0, lh1);
+        const __nv_bfloat16* r0 = xin + (long)h0 * w * ldx + cg * 8;
+        const __nv_bfloat16* r1 = xin + (long)h1 * w * ldx + cg * 8;
+        float v00[8], v01[8], v10[8], v11[8];
+        unpack8(*reinterpret_cast<const uint4*>(r0 + (long)w0 * ldx), v00);
+        unpack8(*reinterpret_cast<const uint4*>(r0 + (long)w1 * ldx), v01);
+        unpack8(*reinterpret_cast<const uint4*>(r1 + (long)w0 * ldx), v10);
+        unpack8(*reinterpret_cast<const uint4*>(r1 + (long)w1 * ldx), v11);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        for (int j = 0; j < 8; ++j)
+          o[j] = lh0 * (lw0 * v00[j] + lw1 * v01[j]) + lh1 * (lw0 * v10[j] + lw1 * v11[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(out + (((long)n * Ho + ho) * Wo + wo) * ldo + cg * 8) = pack8(o);
     }
-    *reinterpret_cast<uint4*>(orow + (long)wo * ldo + cg * 8) = pack8(o);
   }
 }
 
@@ -809,7 +796,7 @@ int fpb200_upsample2x_pad_concat_fwd(const void* x, long ldx, void* out, long ld
                                      int w, int Ho, int Wo, int C, void* stream) {
   if (C % 8 != 0 || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
   const int pad_top = (Ho - 2 * h) / 2, pad_left = (Wo - 2 * w) / 2;
-  upsample2x_pad_fwd_kernel<<<N * Ho, 256, 0, (cudaStream_t)stream>>>(
+  upsample2x_pad_fwd_kernel<<<N * ((Ho + kUpRows - 1) / kUpRows), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, h, w, Ho, Wo, C / 8, pad_top,
       pad_left, align_corners_ratio(h, 2 * h), align_corners_ratio(w, 2 * w));
   return check_launch("upsample2x_pad_concat_fwd");

@@ -39,9 +39,10 @@ SIGNATURES = {
     "fpb200_bn_relu_bwd_apply": (_i, [_vp, _l, _vp, _l, _vp, _l, _vp, _vp, _vp, _l, _i, _vp]),
     "fpb200_upsample2x_pad_concat_fwd": (_i, [_vp, _l, _vp, _l, _i, _i, _i, _i, _i, _i, _vp]),
     "fpb200_upsample2x_pad_concat_bwd": (_i, [_vp, _l, _vp, _l, _i, _i, _i, _i, _i, _i, _vp]),
-    "fpb200_head1x1_fwd": (_i, [_vp, _l, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fpb200_head1x1_fwd": (_i, [_vp, _l, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fpb200_head_bwd_rows": (_i, []),
-    "fpb200_head1x1_bwd": (_i, [_vp, _vp, _l, _vp, _vp, _l, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fpb200_head1x1_bwd": (_i, [_vp, _vp, _l, _vp, _vp, _l, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
+                                _vp, _vp]),
     "fpb200_ce_rows": (_i, []),
     "fpb200_softmax_ce_argmax_fwd": (_i, [_vp, _vp, _l, _vp, _vp, _vp, _vp, _i, _i, _l, _vp]),
     "fpb200_softmax_ce_bwd": (_i, [_vp, _vp, _l, _vp, _vp, _vp, _i, _i, _l, _vp]),

@@ -22,11 +22,17 @@ __device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
 __global__ void __launch_bounds__(256)
 head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const float* __restrict__ w,
                    const float* __restrict__ b, float* __restrict__ logits, int N, long hw,
-                   int ncls) {
+                   int ncls, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift) {
   __shared__ float sw[kMaxClasses * kHeadC];
   __shared__ float sb[kMaxClasses];
+  __shared__ float s_sc[kHeadC], s_sh[kHeadC];
   for (int i = threadIdx.x; i < ncls * kHeadC; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < ncls) sb[threadIdx.x] = b[threadIdx.x];
+  const bool fused_bn = bn_scale != nullptr;   // x is the raw conv output: a = relu(x*scale+shift)
+  if (fused_bn && threadIdx.x < kHeadC) {
+    s_sc[threadIdx.x] = bn_scale[threadIdx.x];
+    s_sh[threadIdx.x] = bn_shift[threadIdx.x];
+  }
   __syncthreads();
   const long total = (long)N * hw;
   for (long px = blockIdx.x * (long)blockDim.x + threadIdx.x; px < total;
@@ -39,6 +45,16 @@ head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const float* _
     for (int g = 0; g < kHeadC / 8; ++g) {
       float f[8];
       unpack8h(__ldg(row + g), f);
+      if (fused_bn) {
+        // same arithmetic and bf16 rounding as bn_apply_relu, so fusing changes no bit
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const uint32_t pk = pack_bf16x2(fmaxf(fmaf(f[j], s_sc[g * 8 + j], s_sh[g * 8 + j]), 0.f),
+                                          fmaxf(fmaf(f[j + 1], s_sc[g * 8 + j + 1], s_sh[g * 8 + j + 1]), 0.f));
+          f[j] = bf16_lo(pk);
+          f[j + 1] = bf16_hi(pk);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < kMaxClasses; ++k) {
         if (k < ncls) {
@@ -62,11 +78,14 @@ head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const float* _
 // ---------------------------------------------------------------------------
 constexpr int kHeadBwdThreads = 256;
 
-template <int NC>
-__global__ void __launch_bounds__(kHeadBwdThreads)
+template <int NC, bool FUSED>
+__global__ void __launch_bounds__(kHeadBwdThreads, 2)
 head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, long ldx,
                    const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, long lddx,
-                   float* __restrict__ partials, int N, long hw, int ncls) {
+                   float* __restrict__ partials, int N, long hw, int ncls,
+                   const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                   const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
+                   float* __restrict__ bn_partials) {
   __shared__ float sw[NC * kHeadC];
   __shared__ float red[(kHeadBwdThreads / 32) * NC * (kHeadC + 1)];
   for (int i = threadIdx.x; i < NC * kHeadC; i += blockDim.x) sw[i] = i < ncls * kHeadC ? w[i] : 0.f;
@@ -74,11 +93,6 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3;  // which pixel of a quad
   const int cg = lane & 7;    // channel group: channels cg*8 .. cg*8+7
-  float wreg[NC][8];
-#pragma unroll
-  for (int k = 0; k < NC; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wreg[k][j] = sw[k * kHeadC + cg * 8 + j];
   float dw[NC][8];
   float db[NC];
 #pragma unroll
@@ -86,6 +100,20 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
     db[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw[k][j] = 0.f;
+  }
+  // fused mode: x is the raw conv output y of the last DoubleConv layer; the activation is
+  // recomputed on load and the layer's BatchNorm-backward sums (sum g, sum g*xhat with
+  // g = dx * [a > 0]) are accumulated here, where dx is produced, instead of in a separate pass
+  // (the second sum is accumulated as sum g*y and converted to sum g*xhat = invstd*(sum g*y -
+  // mean*sum g) once per block, which keeps mean/invstd out of the per-pixel loop)
+  constexpr bool fused_bn = FUSED;
+  float sc[8], sh[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = fused_bn ? __ldg(bn_scale + cg * 8 + j) : 1.f;
+    sh[j] = fused_bn ? __ldg(bn_shift + cg * 8 + j) : 0.f;
+    s1[j] = 0.f;
+    s2[j] = 0.f;
   }
   const long total = (long)N * hw;
   const long warps_total = (long)gridDim.x * (kHeadBwdThreads / 32);
@@ -110,15 +138,29 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (ok[u]) {
-        float f[8], g[8];
+        float f[8], g[8], yraw[8];
         unpack8h(xin[u], f);
+        if (fused_bn) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            yraw[j] = f[j];
+            yraw[j + 1] = f[j + 1];
+            const uint32_t pk = pack_bf16x2(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f),
+                                            fmaxf(fmaf(f[j + 1], sc[j + 1], sh[j + 1]), 0.f));
+            f[j] = bf16_lo(pk);
+            f[j + 1] = bf16_hi(pk);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = 0.f;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(sw + k * kHeadC + cg * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(sw + k * kHeadC + cg * 8 + 4);
+          const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            g[j] = fmaf(dl[u][k], wreg[k][j], g[j]);
+            g[j] = fmaf(dl[u][k], wk[j], g[j]);
             dw[k][j] = fmaf(dl[u][k], f[j], dw[k][j]);
           }
           db[k] += dl[u][k];
@@ -129,6 +171,17 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
         o4.z = pack_bf16x2(g[4], g[5]);
         o4.w = pack_bf16x2(g[6], g[7]);
         *reinterpret_cast<uint4*>(dx + px[u] * lddx + cg * 8) = o4;
+        if (fused_bn) {
+          // the sums use the bf16-rounded dx that is stored (what the apply pass will read)
+          float gr[8];
+          unpack8h(o4, gr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gg = fmaf(yraw[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
+            s1[j] += gg;
+            s2[j] = fmaf(gg, yraw[j], s2[j]);
+          }
+        }
       }
     }
   }
@@ -158,6 +211,34 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
     float acc = 0.f;
     for (int wv = 0; wv < kHeadBwdThreads / 32; ++wv) acc += red[(wv * NC + k) * stride + c];
     partials[(size_t)blockIdx.x * ncls * stride + i] = acc;
+  }
+  if (fused_bn) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+    }
+    __syncthreads();   // `red` is reused: [warp][2][64]
+    if (sub == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red[(warp * 2 + 0) * kHeadC + cg * 8 + j] = s1[j];
+        red[(warp * 2 + 1) * kHeadC + cg * 8 + j] = s2[j];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < kHeadC; c += blockDim.x) {
+      float a1 = 0.f, a2 = 0.f;
+      for (int wv = 0; wv < kHeadBwdThreads / 32; ++wv) {
+        a1 += red[(wv * 2 + 0) * kHeadC + c];
+        a2 += red[(wv * 2 + 1) * kHeadC + c];
+      }
+      bn_partials[(size_t)blockIdx.x * 2 * kHeadC + c] = a1;                                   // sum g
+      bn_partials[(size_t)blockIdx.x * 2 * kHeadC + kHeadC + c] =
+          __ldg(bn_invstd + c) * (a2 - __ldg(bn_mean + c) * a1);                               // sum g*xhat
+    }
   }
 }
 
@@ -377,14 +458,15 @@ using namespace fp;
 extern "C" {
 
 int fpb200_head1x1_fwd(const void* x, long ldx, const float* w, const float* b, float* logits,
-                       int N, int H, int W, int C, int n_classes, void* stream) {
+                       int N, int H, int W, int C, int n_classes, const float* bn_scale,
+                       const float* bn_shift, void* stream) {
   if (C != kHeadC || n_classes < 1 || n_classes > kMaxClasses || ldx % 8 != 0)
     return FPB200_ERR_SHAPE;
   const long total = (long)N * H * W;
   long g = (total + 255) / 256;
   if (g > 148L * 16) g = 148L * 16;
   head1x1_fwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, w, b, logits, N, (long)H * W, n_classes);
+      (const __nv_bfloat16*)x, ldx, w, b, logits, N, (long)H * W, n_classes, bn_scale, bn_shift);
   return check_launch("head1x1_fwd");
 }
 
@@ -392,18 +474,23 @@ int fpb200_head_bwd_rows(void) { return 8 * sm_count(); }
 
 int fpb200_head1x1_bwd(const float* dlogits, const void* x, long ldx, const float* w, void* dx,
                        long lddx, float* dw, float* db, float* partials, int N, int H, int W,
-                       int C, int n_classes, void* stream) {
+                       int C, int n_classes, const float* bn_scale, const float* bn_shift,
+                       const float* bn_mean, const float* bn_invstd, float* bn_partials,
+                       void* stream) {
   if (C != kHeadC || n_classes < 1 || n_classes > kMaxClasses || ldx % 8 != 0 || lddx % 8 != 0)
     return FPB200_ERR_SHAPE;
+  if (bn_scale != nullptr && (!bn_shift || !bn_mean || !bn_invstd || !bn_partials)) return FPB200_ERR_SHAPE;
   const int rows = fpb200_head_bwd_rows();
-  if (n_classes <= 4)
-    head1x1_bwd_kernel<4><<<rows, kHeadBwdThreads, 0, (cudaStream_t)stream>>>(
-        dlogits, (const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)dx, lddx, partials, N,
-        (long)H * W, n_classes);
-  else
-    head1x1_bwd_kernel<8><<<rows, kHeadBwdThreads, 0, (cudaStream_t)stream>>>(
-        dlogits, (const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)dx, lddx, partials, N,
-        (long)H * W, n_classes);
+#define FP_HEAD_BWD(nc, fused)                                                                   \
+  head1x1_bwd_kernel<nc, fused><<<rows, kHeadBwdThreads, 0, (cudaStream_t)stream>>>(             \
+      dlogits, (const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)dx, lddx, partials, N, (long)H * W, \
+      n_classes, bn_scale, bn_shift, bn_mean, bn_invstd, bn_partials)
+  if (n_classes <= 4) {
+    if (bn_scale != nullptr) FP_HEAD_BWD(4, true); else FP_HEAD_BWD(4, false);
+  } else {
+    if (bn_scale != nullptr) FP_HEAD_BWD(8, true); else FP_HEAD_BWD(8, false);
+  }
+#undef FP_HEAD_BWD
   int rc = check_launch("head1x1_bwd");
   if (rc != FPB200_OK) return rc;
   const int n = n_classes * (kHeadC + 1);

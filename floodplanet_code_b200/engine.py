@@ -227,9 +227,11 @@ class UNetEngine:
         stat_rows = ops.stat_rows()
 
         def conv_bn_relu(i: int, xin: torch.Tensor, out_view: Optional[torch.Tensor],
-                         pool_to: Optional[torch.Tensor]) -> torch.Tensor:
+                         pool_to: Optional[torch.Tensor], defer_apply: bool = False):
             """Layer i on xin.  Activation goes to out_view (or a fresh tensor); if pool_to is
-            given the 2x2 max-pool of the activation is written there too."""
+            given the 2x2 max-pool of the activation is written there too.  With defer_apply
+            (training only) the normalise+ReLU pass is left to the consumer kernel and the raw
+            conv output plus its (scale, shift) are returned instead."""
             nonlocal launches
             s = self.specs[i]
             hh, ww = sizes[s.level]
@@ -251,7 +253,9 @@ class UNetEngine:
                                       buffers[f"{s.bn}.running_mean"], buffers[f"{s.bn}.running_var"],
                                       scale, shift, mean, invstd)
                 buffers[f"{s.bn}.num_batches_tracked"].add_(1)
-                if pool_to is not None:
+                if defer_apply:
+                    a = None
+                elif pool_to is not None:
                     idx = torch.empty(pool_to.shape, dtype=torch.uint8, device=dev)
                     ops.bn_apply_relu_maxpool2(y, a, pool_to, idx, scale, shift)
                     if save:
@@ -261,6 +265,8 @@ class UNetEngine:
                 launches += 4  # memset+conv counted as conv(2), finalize, apply
                 if save:
                     st.layers.append(LayerSaved(xin, y, scale, shift, mean, invstd))
+                if defer_apply:
+                    return y, scale, shift
             else:
                 ops.bn_fold_eval(gamma, beta, bias, buffers[f"{s.bn}.running_mean"],
                                  buffers[f"{s.bn}.running_var"], BN_EPS, scale, shift)
@@ -293,15 +299,21 @@ class UNetEngine:
             ops.upsample2x_pad_concat_fwd(cur, cat[lvl][..., c:])
             launches += 1
             cur = conv_bn_relu(li, cat[lvl], None, None); li += 1
-            cur = conv_bn_relu(li, cur, None, None); li += 1
+            if lvl == 0 and training:
+                # last layer: its normalise+ReLU is fused into the head kernel (forward) and its
+                # BatchNorm-backward reduction into the head backward -- no activation is stored
+                cur, head_scale, head_shift = conv_bn_relu(li, cur, None, None, defer_apply=True)
+            else:
+                cur, head_scale, head_shift = conv_bn_relu(li, cur, None, None), None, None
+            li += 1
 
         # ---------------- head ----------------
         logits = torch.empty((n, self.n_classes, h, w), **f32)
         wh = params["outc.conv.weight"].detach().reshape(self.n_classes, 64)
-        ops.head1x1_fwd(cur, wh, params["outc.conv.bias"].detach(), logits)
+        ops.head1x1_fwd(cur, wh, params["outc.conv.bias"].detach(), logits, head_scale, head_shift)
         launches += 1
         if save:
-            st.head_in = cur
+            st.head_in = cur   # raw output y of the last conv (training)
         self.launches = launches
         return logits, st
 
@@ -357,22 +369,31 @@ class UNetEngine:
         d_cur = torch.empty((n, h0, w0, 64), **bf)
         parts = torch.empty((ops.head_bwd_rows(), self.n_classes * 65), **f32)
         wh = params["outc.conv.weight"].detach().reshape(self.n_classes, 64)
+        last = st.layers[-1]
+        head_bn_parts = torch.empty((ops.head_bwd_rows(), 2, 64), **f32)
         ops.head1x1_bwd(dlogits.contiguous(), st.head_in, wh, d_cur,
                         grads["outc.conv.weight"].view(self.n_classes, 64), grads["outc.conv.bias"],
-                        parts)
+                        parts, bn=(last.scale, last.shift, last.mean, last.invstd),
+                        bn_partials=head_bn_parts)
         launches += 2
         mark_ready("outc.conv.weight")
 
         bn_rows = ops.bn_bwd_rows()
 
         def layer_backward(i: int, da: torch.Tensor, need_dx: bool,
-                           dx_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+                           dx_out: Optional[torch.Tensor] = None,
+                           bn_parts: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+            """bn_parts: BatchNorm-backward partial sums already produced by the kernel that
+            wrote `da` (then the separate reduction pass is skipped)."""
             nonlocal launches
             s = self.specs[i]
             sv = st.layers[i]
             hh, ww = sizes[s.level]
-            parts = torch.empty((bn_rows, 2, s.cout), **f32)
-            ops.bn_relu_bwd_reduce(da, sv.y, sv.scale, sv.shift, sv.mean, sv.invstd, parts)
+            if bn_parts is not None:
+                parts = bn_parts
+            else:
+                parts = torch.empty((bn_rows, 2, s.cout), **f32)
+                ops.bn_relu_bwd_reduce(da, sv.y, sv.scale, sv.shift, sv.mean, sv.invstd, parts)
             coef = torch.empty((2, s.cout), **f32)
             ops.bn_bwd_finalize(parts, n * hh * ww, sv.scale, sv.mean, sv.invstd,
                                 grads[f"{s.bn}.weight"], grads[f"{s.bn}.bias"], coef)
@@ -403,7 +424,7 @@ class UNetEngine:
         for lvl in (0, 1, 2, 3):
             c = enc_ch[lvl]
             hh, ww = sizes[lvl]
-            d_mid = layer_backward(li, d_cur, True); li -= 1
+            d_mid = layer_backward(li, d_cur, True, bn_parts=head_bn_parts if lvl == 0 else None); li -= 1
             dcat[lvl] = torch.empty((n, hh, ww, 2 * c), **bf)
             layer_backward(li, d_mid, True, dcat[lvl]); li -= 1
             hl, wl = sizes[lvl + 1]

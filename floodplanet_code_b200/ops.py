@@ -258,22 +258,27 @@ def upsample2x_pad_concat_bwd(dout, dx) -> None:
 
 
 # ------------------------------------------------------------------------------------------
-def head1x1_fwd(x, w, b, logits) -> None:
+def head1x1_fwd(x, w, b, logits, bn_scale=None, bn_shift=None) -> None:
+    """With bn_scale/bn_shift, x is the raw conv output and relu(x*scale+shift) is fused in."""
     xp, ldx = nhwc_view(x)
     n, h, wd, c = x.shape
     ncls = w.shape[0]
     st = _lib().fpb200_head1x1_fwd(xp, ldx, w.data_ptr(), b.data_ptr(), logits.data_ptr(), n, h, wd, c,
-                                   ncls, _stream())
+                                   ncls, _ptr(bn_scale), _ptr(bn_shift), _stream())
     capi.check(st, "head1x1_fwd", N=n, H=h, W=wd, C=c, n_classes=ncls)
 
 
-def head1x1_bwd(dlogits, x, w, dx, dw, db, partials) -> None:
+def head1x1_bwd(dlogits, x, w, dx, dw, db, partials, bn=None, bn_partials=None) -> None:
+    """bn = (scale, shift, mean, invstd) of the layer whose RAW output x is: fuses the activation
+    recompute and that layer's BatchNorm-backward reduction (-> bn_partials [rows][2][C])."""
     xp, ldx = nhwc_view(x)
     dxp, lddx = nhwc_view(dx)
     n, h, wd, c = x.shape
     ncls = w.shape[0]
+    sc, sh, mu, istd = bn if bn is not None else (None, None, None, None)
     st = _lib().fpb200_head1x1_bwd(dlogits.data_ptr(), xp, ldx, w.data_ptr(), dxp, lddx, dw.data_ptr(),
-                                   db.data_ptr(), partials.data_ptr(), n, h, wd, c, ncls, _stream())
+                                   db.data_ptr(), partials.data_ptr(), n, h, wd, c, ncls, _ptr(sc),
+                                   _ptr(sh), _ptr(mu), _ptr(istd), _ptr(bn_partials), _stream())
     capi.check(st, "head1x1_bwd", N=n, H=h, W=wd, C=c, n_classes=ncls)
 
 

@@ -181,15 +181,25 @@ int fpb200_upsample2x_pad_concat_bwd(const void* dout, long lddo, void* dx, long
  * OutConv 1x1 head  -- models/unet.py:70-77
  * ---------------------------------------------------------------------------------------- */
 
-/* logits[n,k,h,w] (fp32 NCHW) = sum_c x[n,h,w,c]*w[k,c] + b[k];  C = 64, n_classes <= 8. */
+/* logits[n,k,h,w] (fp32 NCHW) = sum_c a[n,h,w,c]*w[k,c] + b[k];  C = 64, n_classes <= 8.
+ * bn_scale/bn_shift NULL: x is the activation a.  Non-NULL (training): x is the RAW output y of
+ * the last conv3x3 and a = relu(y*scale+shift) (rounded to bf16) is formed on load, so the
+ * separate BatchNorm-apply pass of that layer (4 B/element) never runs. */
 int fpb200_head1x1_fwd(const void* x, long ldx, const float* w, const float* b, float* logits,
-                       int N, int H, int W, int C, int n_classes, void* stream);
-/* dx (bf16 NHWC), and per-block partials of dW [n_classes][C] and db [n_classes] in
- * `partials` (fp32 [fpb200_head_bwd_rows()][n_classes*(C+1)]), reduced into dw/db. */
+                       int N, int H, int W, int C, int n_classes, const float* bn_scale,
+                       const float* bn_shift, void* stream);
+/* dx (bf16 NHWC, gradient w.r.t. the activation a), and per-block partials of dW [n_classes][C]
+ * and db [n_classes] in `partials` (fp32 [fpb200_head_bwd_rows()][n_classes*(C+1)]), reduced
+ * into dw/db.  With the bn_* pointers non-NULL x is again the raw conv output: a is recomputed
+ * on load and the BatchNorm-backward sums of that layer (sum g, sum g*xhat, g = dx*[a>0]) are
+ * written to bn_partials (fp32 [fpb200_head_bwd_rows()][2][C]) -- the input of
+ * fpb200_bn_bwd_finalize -- so fpb200_bn_relu_bwd_reduce is not needed for that layer. */
 int fpb200_head_bwd_rows(void);
 int fpb200_head1x1_bwd(const float* dlogits, const void* x, long ldx, const float* w, void* dx,
                        long lddx, float* dw, float* db, float* partials, int N, int H, int W,
-                       int C, int n_classes, void* stream);
+                       int C, int n_classes, const float* bn_scale, const float* bn_shift,
+                       const float* bn_mean, const float* bn_invstd, float* bn_partials,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Masked cross-entropy + argmax (+ confusion counts)

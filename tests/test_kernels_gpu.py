@@ -338,6 +338,44 @@ def test_head_fwd_bwd(ops, ncls):
     assert rel(db, br.grad) < 1e-4
 
 
+def test_head_fused_bn_apply_and_bn_bwd_reduce(ops):
+    """Head kernels consuming the RAW last-conv output: forward == head(bn_apply_relu(y)) bit for
+    bit; backward also emits that layer's BatchNorm-backward sums (== the separate reduce pass)."""
+    n, h, w, c, ncls = 2, 20, 24, 64, 3
+    y = rand_act(n, h, w, c, 40)
+    g = torch.Generator(device="cuda").manual_seed(41)
+    scale = torch.rand(c, generator=g, device="cuda") + 0.5
+    shift = torch.randn(c, generator=g, device="cuda") * 0.3
+    mean = torch.randn(c, generator=g, device="cuda") * 0.2
+    invstd = torch.rand(c, generator=g, device="cuda") + 0.5
+    wt = torch.randn(ncls, c, generator=g, device="cuda") / 8
+    b = torch.randn(ncls, generator=g, device="cuda")
+    a = torch.empty_like(y)
+    ops.bn_apply_relu(y, a, scale, shift)
+    l_ref = torch.empty(n, ncls, h, w, device="cuda")
+    l_fused = torch.empty_like(l_ref)
+    ops.head1x1_fwd(a, wt, b, l_ref)
+    ops.head1x1_fwd(y, wt, b, l_fused, scale, shift)
+    assert torch.equal(l_ref, l_fused)
+    dl = torch.randn(n, ncls, h, w, generator=g, device="cuda") * 1e-3
+    outs = []
+    for fused in (False, True):
+        dx = torch.empty_like(y)
+        dw = torch.empty(ncls, c, device="cuda")
+        db = torch.empty(ncls, device="cuda")
+        parts = torch.empty(ops.head_bwd_rows(), ncls * (c + 1), device="cuda")
+        bnp = torch.zeros(ops.head_bwd_rows(), 2, c, device="cuda")
+        if fused:
+            ops.head1x1_bwd(dl, y, wt, dx, dw, db, parts, bn=(scale, shift, mean, invstd), bn_partials=bnp)
+        else:
+            ops.head1x1_bwd(dl, a, wt, dx, dw, db, parts)
+        outs.append((dx, dw, db, bnp))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    ref_parts = torch.empty(ops.bn_bwd_rows(), 2, c, device="cuda")
+    ops.bn_relu_bwd_reduce(outs[0][0], y, scale, shift, mean, invstd, ref_parts)
+    assert rel(outs[1][3].double().sum(0), ref_parts.double().sum(0)) < 1e-5
+
+
 def _ce(ops, logits, target, ignore_index):
     n, ncls = logits.shape[:2]
     result = torch.empty(4, dtype=torch.float64, device="cuda")

@@ -25,7 +25,8 @@ SIGNATURES = {
     "fpb200_conv_stat_rows": (_i, []),
     "fpb200_conv3x3_fprop_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "fpb200_conv3x3_pertap_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
-    "fpb200_conv3x3_dgrad_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp]),
+    "fpb200_conv3x3_dgrad_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp, _vp,
+                                            _vp, _vp]),
     "fpb200_conv3x3_wgrad_workspace_bytes": (_l, [_i, _i, _i, _i, _i]),
     "fpb200_conv3x3_wgrad_bf16_nhwc": (_i, [_vp, _l, _vp, _l, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fpb200_bn_stats_finalize": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

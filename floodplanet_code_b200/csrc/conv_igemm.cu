@@ -59,9 +59,12 @@ struct HaloParams {
   int num_patches, num_n_blks;
   __nv_bfloat16* y;
   long ldy;
-  const float* scale;
-  const float* shift;
+  const float* scale;    // stats_mode 0/1: optional epilogue affine; stats_mode 2: BN scale of the
+  const float* shift;    //   layer whose gradient this dgrad produces (with mean / invstd below)
+  const float* bn_mean;
+  const float* bn_invstd;
   int relu;
+  int stats_mode;        // 0 none, 1 BatchNorm forward sums (y, y^2), 2 BatchNorm backward sums (g, g*xhat)
   float* stat_partials;  // [fpb200_conv_stat_rows()][2][Cout], row = CTA * epilogue warps + warp
 };
 
@@ -75,20 +78,24 @@ struct HaloCfg {
   static constexpr int kABytes = kBoxRows * kRowBytes;             // bytes the TMA writes
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;    // ring pitch
   static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kNB = BN >= 128 ? 6 : 12;                   // weight ring depth (<= 16)
+  static constexpr int kNB = BN >= 128 ? 5 : 8;                    // weight ring depth (<= 16)
   // epilogue warps: one per (TMEM lane quadrant, MMA tile) when the MMAs are short (BN = 64:
   // 32 tensor cycles each, the epilogue is co-critical), one per quadrant otherwise
   static constexpr int kEpiWarps = BN >= 128 ? 4 : 8;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kStgBufs = BN >= 128 ? 2 : 1;               // staging tiles per epilogue warp
+  static constexpr int kStgBufs = 1;                               // output staging tiles per epilogue warp
   static constexpr int kStageOut = kEpiWarps * kStgBufs * 4096;    // epilogue staging, 4 KB tiles
+  // staging for the fused BatchNorm-backward reduction (dgrad): the y tile of the layer being
+  // differentiated, TMA-loaded per (tile, unit); ping-pong when a warp walks several units
+  static constexpr int kYBufs = BN >= 128 ? 2 : 1;
+  static constexpr int kStageY = kEpiWarps * kYBufs * 4096;
   static constexpr int kBudget = 212 * 1024;
-  static constexpr int kNARaw = (kBudget - kStageOut - kNB * kBBytes) / kASlot;
+  static constexpr int kNARaw = (kBudget - kStageOut - kStageY - kNB * kBBytes) / kASlot;
   static constexpr int kNA = kNARaw > 4 ? 4 : kNARaw;
   static constexpr int kTmemCols = 4 * BN <= 256 ? 256 : 512;
   static constexpr int kRingBytes = kNA * kASlot + ((kNB * kBBytes + 1023) / 1024 * 1024);
-  static constexpr int kDataBytes = kRingBytes + kStageOut;
-  static constexpr int kSmemBytes = kDataBytes + 1024 + 512 + 2 * 512 * 4;
+  static constexpr int kDataBytes = kRingBytes + kStageOut + kStageY;
+  static constexpr int kSmemBytes = kDataBytes + 1024 + 1024 + 4 * 512 * 4;
   static_assert(kNA >= 2, "need at least two activation slots");
   static_assert(4 * BN <= 512, "TMEM: 2 tiles x 2 stages x BN columns");
 };
@@ -96,7 +103,8 @@ struct HaloCfg {
 template <int BN, int KCH>
 __global__ void __launch_bounds__(HaloCfg<BN, KCH>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
+                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYL,
+                    const HaloParams p) {
   using Cfg = HaloCfg<BN, KCH>;
   constexpr int kNA = Cfg::kNA, kNB = Cfg::kNB;
   constexpr uint32_t kRB = Cfg::kRowBytes;
@@ -109,6 +117,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + kNA * Cfg::kASlot;
   const uint32_t stg_base = smem_base + Cfg::kRingBytes;
+  const uint32_t ystg_base = stg_base + Cfg::kStageOut;
   const uint32_t bar_base = smem_base + Cfg::kDataBytes;
   auto afull = [&](int s) { return bar_base + 8u * s; };            // 4
   auto aempty = [&](int s) { return bar_base + 32u + 8u * s; };     // 4
@@ -117,8 +126,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tfull = [&](int s) { return bar_base + 320u + 8u * s; };     // 2
   auto tempty = [&](int s) { return bar_base + 336u + 8u * s; };    // 2
   const uint32_t tmem_slot = bar_base + 352u;
-  float* s_scale = reinterpret_cast<float*>(smem_al + Cfg::kDataBytes + 512);
+  auto ybar = [&](int w, int b) { return bar_base + 384u + 8u * (w * 2 + b); };   // 16
+  float* s_scale = reinterpret_cast<float*>(smem_al + Cfg::kDataBytes + 1024);
   float* s_shift = s_scale + 512;
+  float* s_mean = s_scale + 1024;
+  float* s_invstd = s_scale + 1536;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,9 +141,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmY);
+    if (p.stats_mode == 2) tma_prefetch_desc(&tmYL);
     for (int s = 0; s < kNA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < kNB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), Cfg::kEpiWarps); }
+    for (int s = 0; s < 16; ++s) mbar_init(bar_base + 384u + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -139,6 +153,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int c = threadIdx.x; c < p.Cout; c += Cfg::kThreads) {
       s_scale[c] = p.scale[c];
       s_shift[c] = p.shift[c];
+      if (p.stats_mode == 2) {
+        s_mean[c] = p.bn_mean[c];
+        s_invstd[c] = p.bn_invstd[c];
+      }
     }
   }
   tc_fence_before();
@@ -234,11 +252,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp - 2;
     constexpr int kTilesPerWarp = Cfg::kEpiWarps == 8 ? 1 : 2;
     const int t_first = Cfg::kEpiWarps == 8 ? (ew >> 2) : 0;   // 8 warps: warps 2-5 tile 0, 6-9 tile 1
-    const bool do_stats = p.stat_partials != nullptr;
-    const bool do_affine = p.scale != nullptr;
+    const int stats_mode = p.stat_partials != nullptr ? p.stats_mode : 0;
+    const bool do_stats = stats_mode != 0;
+    const bool do_affine = p.scale != nullptr && stats_mode != 2;
     const uint32_t stg0 = stg_base + ew * (Cfg::kStgBufs * 4096);   // this warp's staging tile(s)
+    const uint32_t ystg0 = ystg_base + ew * (Cfg::kYBufs * 4096);   // ... and its y tile(s)
     uint32_t stg_sel = 0;
+    uint32_t ybuf_issue = 0, ybuf_use = 0, yphase = 0;              // y-tile ping-pong state (bit b = parity of buffer b)
     constexpr int kUnits = BN / 64;
+    constexpr int kUnitsPerItem = kTilesPerWarp * kUnits;
     float acc_sum[kUnits][2], acc_sq[kUnits][2];
 #pragma unroll
     for (int u = 0; u < kUnits; ++u) { acc_sum[u][0] = acc_sum[u][1] = acc_sq[u][0] = acc_sq[u][1] = 0.f; }
@@ -268,6 +290,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ph = t2 % p.patches_h;
       const int img = t2 / p.patches_h;
       if (n_blk != cur_n_blk) { flush_stats(); cur_n_blk = n_blk; }
+      // fused BatchNorm-backward: fetch the y tile of unit `k` of this item (same box as the
+      // store) into the next ping-pong buffer; issued one unit ahead so the latency hides behind
+      // the MMA wait / the previous unit's work
+      auto issue_y = [&](int k) {
+        const int t = t_first + k / kUnits, u = k % kUnits;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(ybar(ew, ybuf_issue), 4096);
+          tma_load_4d(ystg0 + ybuf_issue * 4096, &tmYL, ybar(ew, ybuf_issue), n_blk * BN + u * 64,
+                      pw * kPatch + t * 8, ph * kPatch + quad * 4, img);
+        }
+        ybuf_issue = (ybuf_issue + 1) % Cfg::kYBufs;
+      };
+      if (stats_mode == 2) issue_y(0);   // all lanes finished reading this buffer: loop-top __syncwarp of the last unit
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull(as), aphase);
@@ -291,6 +326,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) tma_store_wait_read();
           }
           __syncwarp();
+          if (stats_mode == 2 && Cfg::kYBufs == 2) {
+            const int k = tt * kUnits + u;
+            if (k + 1 < kUnitsPerItem) issue_y(k + 1);   // the other buffer was released by the __syncwarp above
+          }
 #pragma unroll
           for (int hlf = 0; hlf < 2; ++hlf) {
             uint32_t r[32];
@@ -325,7 +364,35 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                          ph * kPatch + quad * 4, img);
             tma_store_commit();
           }
-          if (do_stats) {
+          if (stats_mode == 2) {
+            // BatchNorm-backward sums of the layer whose activation gradient this dgrad writes:
+            //   g = dx * [y*scale+shift > 0],  sum g  and  sum g*xhat,  xhat = (y-mean)*invstd
+            // dx = the staged bf16 tile, y = the TMA-loaded tile of the same box.
+            const uint32_t ybuf = ystg0 + ybuf_use * 4096;
+            mbar_wait(ybar(ew, ybuf_use), (yphase >> ybuf_use) & 1u);
+            yphase ^= 1u << ybuf_use;
+            ybuf_use = (ybuf_use + 1) % Cfg::kYBufs;
+            const int cb = n_blk * BN + u * 64 + 2 * lane;
+            const float sc0 = s_scale[cb], sc1 = s_scale[cb + 1], sh0 = s_shift[cb], sh1 = s_shift[cb + 1];
+            const float mu0 = s_mean[cb], mu1 = s_mean[cb + 1], is0 = s_invstd[cb], is1 = s_invstd[cb + 1];
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              if ((vmask >> rr) & 1u) {
+                const uint32_t off = rr * 128 + (uint32_t((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4;
+                const uint32_t gv = ld_shared_u32(stg + off);
+                const uint32_t yv = ld_shared_u32(ybuf + off);
+                const float y0 = bf16_lo(yv), y1 = bf16_hi(yv);
+                const float g0 = fmaf(y0, sc0, sh0) > 0.f ? bf16_lo(gv) : 0.f;
+                const float g1 = fmaf(y1, sc1, sh1) > 0.f ? bf16_hi(gv) : 0.f;
+                s0 += g0; s1 += g1;
+                q0 = fmaf(g0, (y0 - mu0) * is0, q0);
+                q1 = fmaf(g1, (y1 - mu1) * is1, q1);
+              }
+            }
+            acc_sum[u][0] += s0; acc_sum[u][1] += s1;
+            acc_sq[u][0] += q0; acc_sq[u][1] += q1;
+          } else if (do_stats) {
             // lane l owns channels 2l, 2l+1 of this unit: walk the 32 staged rows
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
@@ -362,7 +429,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <int BN, int KCH>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
-                       const HaloParams& p, cudaStream_t stream) {
+                       const CUtensorMap& tmYL, const HaloParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, KCH>;
   auto kern = conv3x3_halo_kernel<BN, KCH>;
   static bool attr_set = false;
@@ -375,13 +442,17 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int items = p.num_patches * p.num_n_blks;
   int grid = sm_count();
   if (grid > items) grid = items;
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmY, tmYL, p);
   return check_launch("conv3x3_halo");
 }
 
+// bn_y (nullable): dgrad only -- raw conv output of the layer whose activation gradient is being
+// produced; with it scale/shift/bn_mean/bn_invstd are that layer's BatchNorm coefficients and
+// stat_partials receives its backward sums (sum g, sum g*xhat).
 static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, long ldy, int N,
                             int H, int W, int Cin, int Cout, const float* scale, const float* shift,
-                            int relu, float* stat_partials, cudaStream_t stream) {
+                            int relu, float* stat_partials, const void* bn_y, long ld_bn_y,
+                            const float* bn_mean, const float* bn_invstd, cudaStream_t stream) {
   if (N <= 0 || H <= 0 || W <= 0) return FPB200_ERR_SHAPE;
   if (Cin % 16 != 0 || Cout % 64 != 0 || Cout > 2048) return FPB200_ERR_SHAPE;
   if ((ldx % 8) != 0 || (ldy % 8) != 0 || ldx < Cin || ldy < Cout) return FPB200_ERR_SHAPE;
@@ -389,6 +460,9 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
       (reinterpret_cast<uintptr_t>(w_packed) & 15))
     return FPB200_ERR_ALIGN;
   if (scale != nullptr && Cout > 512) return FPB200_ERR_SHAPE;
+  if (bn_y != nullptr && (!scale || !shift || !bn_mean || !bn_invstd || !stat_partials || ld_bn_y % 8 != 0 ||
+                          ld_bn_y < Cout || (reinterpret_cast<uintptr_t>(bn_y) & 15)))
+    return FPB200_ERR_SHAPE;
   const int KCH = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
   const int BN = (Cout % 128 == 0) ? 128 : 64;
 
@@ -401,6 +475,8 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.ldy = ldy;
   p.scale = scale; p.shift = shift; p.relu = relu;
+  p.bn_mean = bn_mean; p.bn_invstd = bn_invstd;
+  p.stats_mode = stat_partials == nullptr ? 0 : (bn_y != nullptr ? 2 : 1);
   p.stat_partials = stat_partials;
 
   CUtensorMap tmA, tmB, tmY;
@@ -410,13 +486,18 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
   if (rc != FPB200_OK) return rc;
   rc = make_tmap_act(&tmY, y, N, H, W, Cout, ldy, 64, 8, 4);  // epilogue store box: 8 px x 4 rows x 64 ch
   if (rc != FPB200_OK) return rc;
+  CUtensorMap tmYL = tmY;
+  if (bn_y != nullptr) {
+    rc = make_tmap_act(&tmYL, bn_y, N, H, W, Cout, ld_bn_y, 64, 8, 4);
+    if (rc != FPB200_OK) return rc;
+  }
   if (stat_partials != nullptr) {
     if (cudaMemsetAsync(stat_partials, 0, (size_t)fpb200_conv_stat_rows() * 2 * Cout * sizeof(float),
                         stream) != cudaSuccess)
       return check_launch("conv3x3 stat memset");
   }
 #define FP_HALO_CASE(bn, kch) \
-  if (BN == bn && KCH == kch) return launch_halo<bn, kch>(tmA, tmB, tmY, p, stream);
+  if (BN == bn && KCH == kch) return launch_halo<bn, kch>(tmA, tmB, tmY, tmYL, p, stream);
   FP_HALO_CASE(128, 64)
   FP_HALO_CASE(64, 64)
   FP_HALO_CASE(128, 32)
@@ -446,16 +527,21 @@ int fpb200_conv3x3_fprop_bf16_nhwc(const void* x, long ldx, const void* w_packed
                                    const float* shift, int relu, float* stat_partials,
                                    void* stream) {
   return fp::conv3x3_dispatch(x, ldx, w_packed, y, ldy, N, H, W, Cin, Cout, scale, shift, relu,
-                              stat_partials, static_cast<cudaStream_t>(stream));
+                              stat_partials, nullptr, 0, nullptr, nullptr,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int fpb200_conv3x3_dgrad_bf16_nhwc(const void* dy, long lddy, const void* w_packed_dgrad, void* dx,
                                    long lddx, int N, int H, int W, int Cout, int Cin,
-                                   void* stream) {
+                                   const void* bn_y, long ld_bn_y, const float* bn_scale,
+                                   const float* bn_shift, const float* bn_mean,
+                                   const float* bn_invstd, float* bn_partials, void* stream) {
   // dgrad of a 3x3/pad-1 conv is the same convolution with the channel roles swapped and
   // the filter rotated by 180 degrees; the rotation/transposition lives in the packing.
-  return fp::conv3x3_dispatch(dy, lddy, w_packed_dgrad, dx, lddx, N, H, W, Cout, Cin, nullptr,
-                              nullptr, 0, nullptr, static_cast<cudaStream_t>(stream));
+  return fp::conv3x3_dispatch(dy, lddy, w_packed_dgrad, dx, lddx, N, H, W, Cout, Cin,
+                              bn_y ? bn_scale : nullptr, bn_y ? bn_shift : nullptr, 0,
+                              bn_y ? bn_partials : nullptr, bn_y, ld_bn_y, bn_mean, bn_invstd,
+                              static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

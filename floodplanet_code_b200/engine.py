@@ -379,6 +379,8 @@ class UNetEngine:
         mark_ready("outc.conv.weight")
 
         bn_rows = ops.bn_bwd_rows()
+        stat_rows_bwd = ops.stat_rows()
+        fused_parts: Dict[int, torch.Tensor] = {}
 
         def layer_backward(i: int, da: torch.Tensor, need_dx: bool,
                            dx_out: Optional[torch.Tensor] = None,
@@ -389,6 +391,8 @@ class UNetEngine:
             s = self.specs[i]
             sv = st.layers[i]
             hh, ww = sizes[s.level]
+            if bn_parts is None:
+                bn_parts = fused_parts.pop(i, None)
             if bn_parts is not None:
                 parts = bn_parts
             else:
@@ -412,7 +416,21 @@ class UNetEngine:
             if need_dx:
                 dx = dx_out if dx_out is not None else torch.empty((n, hh, ww, s.cin), **bf)
                 wd = self.packed.dgrad(s.conv, params[f"{s.conv}.weight"])
-                self._timed("dgrad", i, n, hh * ww, lambda: ops.conv3x3_dgrad(dy, wd, dx))
+                if i % 2 == 1 and dx_out is None and (s.cin == 64 or s.cout >= 256):
+                    # second conv of a DoubleConv: dx IS the activation gradient of layer i-1, so
+                    # that layer's BatchNorm-backward reduction rides in this dgrad's epilogue.
+                    # (Measured: pays off when the epilogue has slack -- 8 epilogue warps for
+                    # 64-channel outputs, or >= 2304-deep GEMMs; for the 128-channel layers with
+                    # short K the epilogue becomes critical and the separate pass is cheaper.)
+                    pv = st.layers[i - 1]
+                    fparts = torch.empty((stat_rows_bwd, 2, s.cin), **f32)
+                    self._timed("dgrad", i, n, hh * ww,
+                                lambda: ops.conv3x3_dgrad(dy, wd, dx, bn_y=pv.y,
+                                                          bn=(pv.scale, pv.shift, pv.mean, pv.invstd),
+                                                          bn_partials=fparts))
+                    fused_parts[i - 1] = fparts
+                else:
+                    self._timed("dgrad", i, n, hh * ww, lambda: ops.conv3x3_dgrad(dy, wd, dx))
                 launches += 1
             mark_ready(f"{s.conv}.weight")
             return dx

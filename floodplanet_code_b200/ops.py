@@ -125,14 +125,21 @@ def conv3x3_fprop(x: torch.Tensor, w_packed: torch.Tensor, y: torch.Tensor,
     capi.check(st, "conv3x3_fprop_bf16_nhwc", N=n, H=h, W=w, Cin=cin, Cout=cout)
 
 
-def conv3x3_dgrad(dy: torch.Tensor, w_packed_dgrad: torch.Tensor, dx: torch.Tensor) -> None:
+def conv3x3_dgrad(dy: torch.Tensor, w_packed_dgrad: torch.Tensor, dx: torch.Tensor,
+                  bn_y: Optional[torch.Tensor] = None, bn=None,
+                  bn_partials: Optional[torch.Tensor] = None) -> None:
+    """bn_y / bn=(scale, shift, mean, invstd) / bn_partials: fuse the BatchNorm-backward
+    reduction of the layer whose activation gradient `dx` is (see the header)."""
     _require_cuda(dy, w_packed_dgrad, dx)
     dyp, lddy = nhwc_view(dy)
     dxp, lddx = nhwc_view(dx)
     n, h, w, cout = dy.shape
     cin = dx.shape[3]
+    byp, ldby = nhwc_view(bn_y) if bn_y is not None else (None, 0)
+    sc, sh, mu, istd = bn if bn is not None else (None, None, None, None)
     st = _lib().fpb200_conv3x3_dgrad_bf16_nhwc(dyp, lddy, w_packed_dgrad.data_ptr(), dxp, lddx, n, h,
-                                               w, cout, cin, _stream())
+                                               w, cout, cin, byp, ldby, _ptr(sc), _ptr(sh), _ptr(mu),
+                                               _ptr(istd), _ptr(bn_partials), _stream())
     capi.check(st, "conv3x3_dgrad_bf16_nhwc", N=n, H=h, W=w, Cout=cout, Cin=cin)
 
 

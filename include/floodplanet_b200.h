@@ -91,10 +91,18 @@ int fpb200_conv3x3_pertap_bf16_nhwc(const void* x, long ldx, const void* w_packe
                                     const float* scale, const float* shift, int relu,
                                     float* stat_partials, void* stream);
 
-/* dx = conv3x3_transpose(dy, w): Cout channels in, Cin (multiple of 64) channels out. */
+/* dx = conv3x3_transpose(dy, w): Cout channels in, Cin (multiple of 64) channels out.
+ * Optional fused BatchNorm-backward reduction (bn_y != NULL): when dx is the gradient w.r.t. the
+ * activation a = relu(bn(y_prev)) of the preceding conv layer, pass that layer's raw output
+ * bn_y (NHWC bf16 view, Cin channels) and its coefficients; the epilogue then also writes the
+ * partial sums  sum g, sum g*xhat  (g = dx*[a>0]) to bn_partials
+ * ([fpb200_conv_stat_rows()][2][Cin] fp32, the input of fpb200_bn_bwd_finalize), replacing
+ * fpb200_bn_relu_bwd_reduce for that layer.  Requires Cin <= 512. */
 int fpb200_conv3x3_dgrad_bf16_nhwc(const void* dy, long lddy, const void* w_packed_dgrad,
                                    void* dx, long lddx, int N, int H, int W, int Cout, int Cin,
-                                   void* stream);
+                                   const void* bn_y, long ld_bn_y, const float* bn_scale,
+                                   const float* bn_shift, const float* bn_mean,
+                                   const float* bn_invstd, float* bn_partials, void* stream);
 
 /* dW = sum_pixels dy (x) shifted x.  Two stages, deterministic:
  *   stage 1 (tensor cores) writes split-K partials into `workspace`

@@ -19,6 +19,7 @@ ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--layers", default="")
 ap.add_argument("--kinds", default="fprop,dgrad,wgrad")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--fused-bn", action="store_true", help="dgrad with the fused BatchNorm-backward reduction")
 args = ap.parse_args()
 
 specs = unet_conv_specs(4)
@@ -46,7 +47,13 @@ for i in layers:
                 continue
             wd = ops.repack_dgrad(w)
             dx = torch.empty(n, hw, hw, s.cin, dtype=torch.bfloat16, device="cuda")
-            fn = lambda: ops.conv3x3_dgrad(dy, wd, dx)
+            if args.fused_bn and s.cin <= 512:
+                yp = torch.randn(n, hw, hw, s.cin, device="cuda").to(torch.bfloat16)
+                co = [torch.rand(s.cin, device="cuda") + 0.5 for _ in range(4)]
+                bp = torch.empty(ops.stat_rows(), 2, s.cin, device="cuda")
+                fn = lambda: ops.conv3x3_dgrad(dy, wd, dx, bn_y=yp, bn=tuple(co), bn_partials=bp)
+            else:
+                fn = lambda: ops.conv3x3_dgrad(dy, wd, dx)
         else:
             dw = torch.empty(s.cout, s.cin, 3, 3, device="cuda")
             ws = torch.empty(ops.wgrad_workspace_bytes(n, hw, hw, cin, s.cout) // 4, device="cuda")

@@ -116,6 +116,33 @@ def test_conv3x3_dgrad(ops, n, h, w, cin, cout):
     assert err < 2e-2, f"dgrad rel err {err}"
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (1, 20, 24, 128, 256), (1, 37, 37, 128, 64),
+                                            (2, 16, 16, 256, 128)])
+def test_conv3x3_dgrad_fused_bn_backward_reduce(ops, n, h, w, cin, cout):
+    """dgrad whose epilogue also reduces the BatchNorm-backward sums of the layer that produced
+    the conv's input: same dx bit for bit, same sums as the separate reduction pass."""
+    dy = rand_act(n, h, w, cout, 50)
+    wt = rand_w(cout, cin, 51)
+    wd = ops.repack_dgrad(wt)
+    y_prev = rand_act(n, h, w, cin, 52)
+    g = torch.Generator(device="cuda").manual_seed(53)
+    scale = torch.rand(cin, generator=g, device="cuda") + 0.5
+    shift = torch.randn(cin, generator=g, device="cuda") * 0.3
+    mean = torch.randn(cin, generator=g, device="cuda") * 0.2
+    invstd = torch.rand(cin, generator=g, device="cuda") + 0.5
+    dx0 = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device="cuda")
+    dx1 = torch.empty_like(dx0)
+    ops.conv3x3_dgrad(dy, wd, dx0)
+    parts = torch.empty(ops.stat_rows(), 2, cin, device="cuda")
+    ops.conv3x3_dgrad(dy, wd, dx1, bn_y=y_prev, bn=(scale, shift, mean, invstd), bn_partials=parts)
+    torch.cuda.synchronize()
+    assert torch.equal(dx0, dx1)
+    ref = torch.empty(ops.bn_bwd_rows(), 2, cin, device="cuda")
+    ops.bn_relu_bwd_reduce(dx0, y_prev, scale, shift, mean, invstd, ref)
+    a, b = parts.double().sum(0), ref.double().sum(0)
+    assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()), (a - b).abs().max()
+
+
 WGRAD_SHAPES = [
     # n, h, w, cin(padded), cin_real, cout
     (2, 16, 16, 128, 128, 128),   # MODE_X_SHIFT, NB=2

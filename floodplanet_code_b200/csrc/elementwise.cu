@@ -300,56 +300,109 @@ bn_apply_relu_maxpool2_kernel(const __nv_bfloat16* __restrict__ y, long ldy,
   }
 }
 
+// FUSED: dx is the activation gradient of a conv+BN+ReLU layer (the skip tensor), so that
+// layer's BatchNorm-backward sums (sum g, sum g*xhat, g = dx*[y*scale+shift > 0]) are reduced
+// right here, where dx is produced, from one extra read of y -- the separate reduction pass
+// (which would read dx and y again) is skipped.  Requires CG | 256, so a thread keeps one
+// channel group for all its windows; blocks walk window rows with a grid stride.
+template <bool FUSED>
 __global__ void __launch_bounds__(256)
 maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dpooled, long lddp,
                     const uint8_t* __restrict__ pool_idx, const __nv_bfloat16* __restrict__ dskip,
-                    long ldds, __nv_bfloat16* __restrict__ dx, long lddx, int H, int W, int CG) {
+                    long ldds, __nv_bfloat16* __restrict__ dx, long lddx, int N, int H, int W, int CG,
+                    const __nv_bfloat16* __restrict__ y, long ldy, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, float* __restrict__ partials) {
+  __shared__ float red[FUSED ? 256 * 16 : 1];
   const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
   const int Hp = H >> 1, Wp = W >> 1;
-  const int n = blockIdx.x / Hc;
-  const int ho = blockIdx.x - n * Hc;
   const int work = Wc * CG;
-  for (int i = threadIdx.x; i < work; i += blockDim.x) {
-    const int wo = i / CG;
-    const int cg = i - wo * CG;
-    const bool has_pool = ho < Hp && wo < Wp;
-    float g[8];
-    uint2 ib = make_uint2(0, 0);
-    uint4 sk[4];
-    bool ok[4];
-    if (has_pool) {
-      const long pp = ((long)n * Hp + ho) * Wp + wo;
-      unpack8(ld_stream(dpooled + pp * lddp + cg * 8), g);
-      ib = *reinterpret_cast<const uint2*>(pool_idx + pp * (long)(CG * 8) + cg * 8);
-    }
+  float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+  if (FUSED) {
+    const int cg0 = threadIdx.x % CG;
+    load8f(scale + cg0 * 8, sc);
+    load8f(shift + cg0 * 8, sh);
+    load8f(mean + cg0 * 8, mu);
+    load8f(invstd + cg0 * 8, is);
 #pragma unroll
-    for (int pos = 0; pos < 4; ++pos) {
-      const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
-      ok[pos] = h < H && w < W;
-      if (ok[pos] && dskip != nullptr)
-        sk[pos] = ld_stream(dskip + (((long)n * H + h) * W + w) * ldds + cg * 8);
-    }
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  }
+  for (int rowi = blockIdx.x; rowi < N * Hc; rowi += gridDim.x) {
+    const int n = rowi / Hc;
+    const int ho = rowi - n * Hc;
+    for (int i = threadIdx.x; i < work; i += blockDim.x) {
+      const int wo = i / CG;
+      const int cg = i - wo * CG;
+      const bool has_pool = ho < Hp && wo < Wp;
+      float g[8];
+      uint2 ib = make_uint2(0, 0);
+      uint4 sk[4], yv[4];
+      bool ok[4];
+      if (has_pool) {
+        const long pp = ((long)n * Hp + ho) * Wp + wo;
+        unpack8(ld_stream(dpooled + pp * lddp + cg * 8), g);
+        ib = *reinterpret_cast<const uint2*>(pool_idx + pp * (long)(CG * 8) + cg * 8);
+      }
 #pragma unroll
-    for (int pos = 0; pos < 4; ++pos) {
-      if (ok[pos]) {
+      for (int pos = 0; pos < 4; ++pos) {
         const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
-        float f[8];
-        if (dskip != nullptr) {
-          unpack8(sk[pos], f);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        ok[pos] = h < H && w < W;
+        if (ok[pos]) {
+          const long px = ((long)n * H + h) * W + w;
+          if (dskip != nullptr) sk[pos] = ld_stream(dskip + px * ldds + cg * 8);
+          if (FUSED) yv[pos] = ld_stream(y + px * ldy + cg * 8);
         }
-        if (has_pool) {
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t word = j < 4 ? ib.x : ib.y;
-            const int sel = (word >> (8 * (j & 3))) & 0xFF;
-            if (sel == pos) f[j] += g[j];
+      for (int pos = 0; pos < 4; ++pos) {
+        if (ok[pos]) {
+          const int h = 2 * ho + (pos >> 1), w = 2 * wo + (pos & 1);
+          float f[8];
+          if (dskip != nullptr) {
+            unpack8(sk[pos], f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+          }
+          if (has_pool) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t word = j < 4 ? ib.x : ib.y;
+              const int sel = (word >> (8 * (j & 3))) & 0xFF;
+              if (sel == pos) f[j] += g[j];
+            }
+          }
+          const uint4 packed = pack8(f);
+          *reinterpret_cast<uint4*>(dx + (((long)n * H + h) * W + w) * lddx + cg * 8) = packed;
+          if (FUSED) {
+            float gr[8], v[8];
+            unpack8(packed, gr);          // the bf16 values the apply pass will read
+            unpack8(yv[pos], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
+              s1[j] += gg;
+              s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
+            }
           }
         }
-        *reinterpret_cast<uint4*>(dx + (((long)n * H + h) * W + w) * lddx + cg * 8) = pack8(f);
       }
+    }
+  }
+  if (FUSED) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[threadIdx.x * 16 + j] = s1[j];
+      red[threadIdx.x * 16 + 8 + j] = s2[j];
+    }
+    __syncthreads();
+    const int TP = 256 / CG;
+    const int C = CG * 8;
+    for (int o = threadIdx.x; o < CG * 16; o += 256) {
+      const int ocg = o >> 4, oj = o & 15;
+      float acc = 0.f;
+      for (int pidx = 0; pidx < TP; ++pidx) acc += red[(pidx * CG + ocg) * 16 + oj];
+      partials[(size_t)blockIdx.x * 2 * C + (oj >> 3) * C + ocg * 8 + (oj & 7)] = acc;
     }
   }
 }
@@ -748,12 +801,32 @@ int fpb200_bn_apply_relu_maxpool2(const void* y, long ldy, void* a, long lda, vo
 }
 
 int fpb200_maxpool2_bwd(const void* dpooled, long lddp, const uint8_t* pool_idx, const void* dskip,
-                        long ldds, void* dx, long lddx, int N, int H, int W, int C, void* stream) {
+                        long ldds, void* dx, long lddx, int N, int H, int W, int C, const void* bn_y,
+                        long ld_bn_y, const float* bn_scale, const float* bn_shift,
+                        const float* bn_mean, const float* bn_invstd, float* bn_partials,
+                        void* stream) {
   if (C % 8 != 0 || lddp % 8 != 0 || lddx % 8 != 0) return FPB200_ERR_SHAPE;
-  maxpool2_bwd_kernel<<<N * ((H + 1) / 2), 256, 0, (cudaStream_t)stream>>>(
+  const int rows = N * ((H + 1) / 2);
+  if (bn_y == nullptr) {
+    maxpool2_bwd_kernel<false><<<rows, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dpooled, lddp, pool_idx, (const __nv_bfloat16*)dskip, ldds,
+        (__nv_bfloat16*)dx, lddx, N, H, W, C / 8, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return check_launch("maxpool2_bwd");
+  }
+  if (256 % (C / 8) != 0 || ld_bn_y % 8 != 0 || !bn_scale || !bn_shift || !bn_mean || !bn_invstd ||
+      !bn_partials)
+    return FPB200_ERR_SHAPE;
+  const int prow = fpb200_bn_bwd_rows() * 2;
+  const int grid = rows < prow ? rows : prow;
+  if (grid < prow &&
+      cudaMemsetAsync(bn_partials + (size_t)grid * 2 * C, 0, (size_t)(prow - grid) * 2 * C * sizeof(float),
+                      (cudaStream_t)stream) != cudaSuccess)
+    return check_launch("maxpool2_bwd memset");
+  maxpool2_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dpooled, lddp, pool_idx, (const __nv_bfloat16*)dskip, ldds,
-      (__nv_bfloat16*)dx, lddx, H, W, C / 8);
-  return check_launch("maxpool2_bwd");
+      (__nv_bfloat16*)dx, lddx, N, H, W, C / 8, (const __nv_bfloat16*)bn_y, ld_bn_y, bn_scale, bn_shift,
+      bn_mean, bn_invstd, bn_partials);
+  return check_launch("maxpool2_bwd_fused");
 }
 
 int fpb200_bn_bwd_rows(void) { return 4 * sm_count(); }

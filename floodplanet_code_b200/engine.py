@@ -456,10 +456,14 @@ class UNetEngine:
             c = enc_ch[lvl]
             hh, ww = sizes[lvl]
             d_skip = torch.empty((n, hh, ww, c), **bf)
-            ops.maxpool2_bwd(d_pool, st.pool_idx[lvl], dcat[lvl][..., :c], d_skip)
+            # the skip layer's BatchNorm-backward reduction rides in the pool-backward pass
+            sk = st.layers[li]
+            pool_parts = torch.empty((2 * bn_rows, 2, c), **f32)
+            ops.maxpool2_bwd(d_pool, st.pool_idx[lvl], dcat[lvl][..., :c], d_skip, bn_y=sk.y,
+                             bn=(sk.scale, sk.shift, sk.mean, sk.invstd), bn_partials=pool_parts)
             launches += 1
             del dcat[lvl]
-            d_mid = layer_backward(li, d_skip, True); li -= 1
+            d_mid = layer_backward(li, d_skip, True, bn_parts=pool_parts); li -= 1
             d_pool = layer_backward(li, d_mid, lvl > 0); li -= 1
         assert li == -1
         if side is not None:

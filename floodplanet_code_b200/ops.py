@@ -206,13 +206,18 @@ def bn_apply_relu_maxpool2(y, a, pooled, pool_idx, scale, shift) -> None:
     capi.check(st, "bn_apply_relu_maxpool2", N=n, H=h, W=w, C=c)
 
 
-def maxpool2_bwd(dpooled, pool_idx, dskip, dx) -> None:
+def maxpool2_bwd(dpooled, pool_idx, dskip, dx, bn_y=None, bn=None, bn_partials=None) -> None:
+    """bn_y / bn=(scale, shift, mean, invstd) / bn_partials ([2*bn_bwd_rows()][2][C]): also reduce the
+    BatchNorm-backward sums of the layer whose activation gradient dx is."""
     dpp, lddp = nhwc_view(dpooled)
     dsp, ldds = nhwc_view(dskip) if dskip is not None else (None, 0)
     dxp, lddx = nhwc_view(dx)
     n, h, w, c = dx.shape
+    byp, ldby = nhwc_view(bn_y) if bn_y is not None else (None, 0)
+    sc, sh, mu, istd = bn if bn is not None else (None, None, None, None)
     st = _lib().fpb200_maxpool2_bwd(dpp, lddp, pool_idx.data_ptr(), dsp, ldds, dxp, lddx, n, h, w, c,
-                                    _stream())
+                                    byp, ldby, _ptr(sc), _ptr(sh), _ptr(mu), _ptr(istd),
+                                    _ptr(bn_partials), _stream())
     capi.check(st, "maxpool2_bwd", N=n, H=h, W=w, C=c)
 
 

@@ -148,9 +148,15 @@ int fpb200_bn_apply_relu_maxpool2(const void* y, long ldy, void* a, long lda, vo
                                   const float* shift, int N, int H, int W, int C, void* stream);
 
 /* MaxPool2d(2) backward fused with the skip-connection gradient add:
- *   dx[n,h,w,c] = dskip[n,h,w,c] (nullable) + (pool_idx selects (h,w)) ? dpooled : 0 */
+ *   dx[n,h,w,c] = dskip[n,h,w,c] (nullable) + (pool_idx selects (h,w)) ? dpooled : 0
+ * Optional (bn_y != NULL): dx is the activation gradient of the conv+BN+ReLU layer whose raw
+ * output is bn_y; that layer's BatchNorm-backward partial sums (as fpb200_bn_relu_bwd_reduce
+ * would produce) are written to bn_partials, fp32 [2*fpb200_bn_bwd_rows()][2][C]. */
 int fpb200_maxpool2_bwd(const void* dpooled, long lddp, const uint8_t* pool_idx, const void* dskip,
-                        long ldds, void* dx, long lddx, int N, int H, int W, int C, void* stream);
+                        long ldds, void* dx, long lddx, int N, int H, int W, int C, const void* bn_y,
+                        long ld_bn_y, const float* bn_scale, const float* bn_shift,
+                        const float* bn_mean, const float* bn_invstd, float* bn_partials,
+                        void* stream);
 
 /* BatchNorm+ReLU backward, pass 1: with g = da * (y*scale+shift > 0) and
  * xhat = (y-mean)*invstd, writes per-block partial sums of g and g*xhat:

@@ -279,6 +279,30 @@ def test_maxpool_bwd_with_skip(ops, n, h, w, c):
     assert torch.equal(nchw(dx), ref)
 
 
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (1, 37, 37, 128), (3, 10, 12, 512)])
+def test_maxpool_bwd_fused_bn_backward_reduce(ops, n, h, w, c):
+    a = rand_act(n, h, w, c, 60)
+    pooled = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device="cuda")
+    idx = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device="cuda")
+    ops.bn_apply_relu_maxpool2(a, None, pooled, idx, None, None)
+    dp = rand_act(n, h // 2, w // 2, c, 61)
+    dcat = rand_act(n, h, w, 2 * c, 62)
+    y = rand_act(n, h, w, c, 63)
+    g = torch.Generator(device="cuda").manual_seed(64)
+    co = [torch.rand(c, generator=g, device="cuda") + 0.5, torch.randn(c, generator=g, device="cuda") * 0.3,
+          torch.randn(c, generator=g, device="cuda") * 0.2, torch.rand(c, generator=g, device="cuda") + 0.5]
+    dx0 = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    dx1 = torch.empty_like(dx0)
+    ops.maxpool2_bwd(dp, idx, dcat[..., :c], dx0)
+    parts = torch.empty(2 * ops.bn_bwd_rows(), 2, c, device="cuda")
+    ops.maxpool2_bwd(dp, idx, dcat[..., :c], dx1, bn_y=y, bn=tuple(co), bn_partials=parts)
+    assert torch.equal(dx0, dx1)
+    ref = torch.empty(ops.bn_bwd_rows(), 2, c, device="cuda")
+    ops.bn_relu_bwd_reduce(dx0, y, co[0], co[1], co[2], co[3], ref)
+    a_, b_ = parts.double().sum(0), ref.double().sum(0)
+    assert float((a_ - b_).abs().max()) <= 1e-4 * float(b_.abs().max())
+
+
 @pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (1, 19, 23, 256), (2, 8, 8, 512)])
 def test_bn_relu_backward(ops, n, h, w, c):
     y = rand_act(n, h, w, c, 18)

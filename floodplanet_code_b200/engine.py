@@ -155,10 +155,12 @@ class UNetEngine:
         self.grad_done_hook: Optional[Callable[[torch.Tensor, int], None]] = None
         # optional profiler: when a list, (tag, flops, start_event, end_event) per conv launch
         self.conv_events: Optional[list] = None
-        # backward: run every wgrad on a second stream.  wgrad is off the critical path (only the
-        # optimiser needs dW) and tensor-bound, so it overlaps the HBM-bound BatchNorm-backward
-        # passes of the next layer, which run on the leftover warps/registers of the same SMs.
-        self.overlap_wgrad = True
+        # backward: optionally run every wgrad on a second stream.  wgrad is off the critical path
+        # (only the optimiser needs dW) and could overlap the HBM-bound BatchNorm-backward passes
+        # of the next layer.  Measured on B200 at batch 64: <= 1 % gain (both kernels are persistent
+        # and the step is power-capped, so overlap buys no energy) and more run-to-run variance
+        # from cross-stream allocator bookkeeping -- off by default.
+        self.overlap_wgrad = False
         self._side_stream: Optional[torch.cuda.Stream] = None
         self.launches = 0  # kernels launched by the last forward/backward (for bench accounting)
 

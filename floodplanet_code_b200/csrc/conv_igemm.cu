@@ -83,8 +83,7 @@ struct HaloCfg {
   // 32 tensor cycles each, the epilogue is co-critical), one per quadrant otherwise
   static constexpr int kEpiWarps = BN >= 128 ? 4 : 8;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kStgBufs = 1;                               // output staging tiles per epilogue warp
-  static constexpr int kStageOut = kEpiWarps * kStgBufs * 4096;    // epilogue staging, 4 KB tiles
+  static constexpr int kStageOut = kEpiWarps * 4096;               // epilogue output staging, one 4 KB tile per warp
   // staging for the fused BatchNorm-backward reduction (dgrad): the y tile of the layer being
   // differentiated, TMA-loaded per (tile, unit); ping-pong when a warp walks several units
   static constexpr int kYBufs = BN >= 128 ? 2 : 1;
@@ -255,9 +254,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int stats_mode = p.stat_partials != nullptr ? p.stats_mode : 0;
     const bool do_stats = stats_mode != 0;
     const bool do_affine = p.scale != nullptr && stats_mode != 2;
-    const uint32_t stg0 = stg_base + ew * (Cfg::kStgBufs * 4096);   // this warp's staging tile(s)
+    const uint32_t stg = stg_base + ew * 4096;                      // this warp's output staging tile
     const uint32_t ystg0 = ystg_base + ew * (Cfg::kYBufs * 4096);   // ... and its y tile(s)
-    uint32_t stg_sel = 0;
     uint32_t ybuf_issue = 0, ybuf_use = 0, yphase = 0;              // y-tile ping-pong state (bit b = parity of buffer b)
     constexpr int kUnits = BN / 64;
     constexpr int kUnitsPerItem = kTilesPerWarp * kUnits;
@@ -316,15 +314,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
         for (int u = 0; u < kUnits; ++u) {
-          // the TMA store issued two units ago must have finished reading this staging tile
-          const uint32_t stg = stg0 + stg_sel * 4096;
+          // the previous TMA store must have finished reading the staging tile (a second,
+          // ping-pong tile was measured to buy nothing: the store drains long before the next
+          // unit's accumulator has been converted)
           const uint32_t stg_row = stg + lane * 128;
-          if (Cfg::kStgBufs == 2) {
-            stg_sel ^= 1u;
-            if (lane == 0) tma_store_wait_read_keep1();
-          } else {
-            if (lane == 0) tma_store_wait_read();
-          }
+          if (lane == 0) tma_store_wait_read();
           __syncwarp();
           if (stats_mode == 2 && Cfg::kYBufs == 2) {
             const int k = tt * kUnits + u;

@@ -14,7 +14,7 @@ only the final uint8 masks (or, for overlapping strides, the canvases) are combi
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import torch
 

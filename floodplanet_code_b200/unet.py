@@ -11,7 +11,7 @@ input raises.
 """
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import Sequence
 
 import torch
 import torch.nn as nn

@@ -9,7 +9,7 @@ to is the B200 engine (UNet kernels + fused masked-CE/argmax/confusion kernel).
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.nn as nn

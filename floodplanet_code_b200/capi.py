@@ -50,6 +50,14 @@ SIGNATURES = {
     "fpb200_softmax_ce_bwd": (_i, [_vp, _vp, _l, _vp, _vp, _vp, _i, _i, _l, _vp]),
     "fpb200_softmax_stitch_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _l, _l, _vp]),
     "fpb200_canvas_to_mask_u8": (_i, [_vp, _vp, _vp, _l, _i, _vp]),
+    "fpb200_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _vp]),
+    "fpb200_nhwc_bf16_to_nchw_f32": (_i, [_vp, _l, _vp, _i, _i, _i, _i, _vp]),
+    "fpb200_repack_weights_1x1": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "fpb200_conv1x1_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "fpb200_conv1x1_wgrad_workspace_bytes": (_l, [_i, _i, _i, _i, _i]),
+    "fpb200_conv1x1_wgrad_bf16_nhwc": (_i, [_vp, _l, _vp, _l, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fpb200_channel_sum_rows": (_i, []),
+    "fpb200_channel_sum_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _vp]),
     "fpb200_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
     "fpb200_adam_step_graphable": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _vp, _f, _vp]),
 }

@@ -69,11 +69,15 @@ struct HaloParams {
 };
 
 constexpr int kPatch = 16;        // patch edge in pixels
-constexpr int kBox = kPatch + 2;  // with halo
-constexpr int kBoxRows = kBox * kBox;
 
-template <int BN, int KCH>
+// TAPS = 9: 3x3 / pad 1 (box = patch + 1-pixel halo); TAPS = 1: pointwise (1x1) convolution,
+// the same pipeline with a halo-free 16 x 16 box and a single "tap".
+template <int BN, int KCH, int TAPS>
 struct HaloCfg {
+  static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
+  static constexpr int kHalo = TAPS == 9 ? 1 : 0;
+  static constexpr int kBox = kPatch + 2 * kHalo;                   // box edge in pixels
+  static constexpr int kBoxRows = kBox * kBox;
   static constexpr int kRowBytes = KCH * 2;
   static constexpr int kABytes = kBoxRows * kRowBytes;             // bytes the TMA writes
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;    // ring pitch
@@ -99,13 +103,14 @@ struct HaloCfg {
   static_assert(4 * BN <= 512, "TMEM: 2 tiles x 2 stages x BN columns");
 };
 
-template <int BN, int KCH>
-__global__ void __launch_bounds__(HaloCfg<BN, KCH>::kThreads, 1)
+template <int BN, int KCH, int TAPS>
+__global__ void __launch_bounds__(HaloCfg<BN, KCH, TAPS>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYL,
                     const HaloParams p) {
-  using Cfg = HaloCfg<BN, KCH>;
+  using Cfg = HaloCfg<BN, KCH, TAPS>;
   constexpr int kNA = Cfg::kNA, kNB = Cfg::kNB;
+  constexpr int kBox = Cfg::kBox, kHalo = Cfg::kHalo;
   constexpr uint32_t kRB = Cfg::kRowBytes;
   constexpr uint32_t kSwz = kRB;
   constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0, 0);
@@ -180,9 +185,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait(aempty(sa), pa ^ 1u);
           mbar_arrive_expect_tx(afull(sa), Cfg::kABytes);
-          tma_load_4d(a_base + sa * Cfg::kASlot, &tmA, afull(sa), kc * KCH, w0 - 1, h0 - 1, img);
+          tma_load_4d(a_base + sa * Cfg::kASlot, &tmA, afull(sa), kc * KCH, w0 - kHalo, h0 - kHalo, img);
           if (++sa == kNA) { sa = 0; pa ^= 1u; }
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < TAPS; ++tap) {
             mbar_wait(bempty(sb), pb ^ 1u);
             mbar_arrive_expect_tx(bfull(sb), Cfg::kBBytes);
             tma_load_2d(b_base + sb * Cfg::kBBytes, &tmB, bfull(sb), tap * p.Cin + kc * KCH,
@@ -212,7 +217,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t a_lo = smem_desc_lo(a_base + sa * Cfg::kASlot, 16);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < TAPS; ++tap) {
             constexpr uint32_t kAHi = smem_desc_hi(kBox * kRB, kSwz);
             constexpr uint32_t kBHi = smem_desc_hi(8 * kRB, kSwz);
             const int r = tap / 3, s = tap - 3 * r;
@@ -421,11 +426,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int KCH>
+template <int BN, int KCH, int TAPS>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                        const CUtensorMap& tmYL, const HaloParams& p, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN, KCH>;
-  auto kern = conv3x3_halo_kernel<BN, KCH>;
+  using Cfg = HaloCfg<BN, KCH, TAPS>;
+  auto kern = conv3x3_halo_kernel<BN, KCH, TAPS>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
@@ -446,9 +451,11 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, long ldy, int N,
                             int H, int W, int Cin, int Cout, const float* scale, const float* shift,
                             int relu, float* stat_partials, const void* bn_y, long ld_bn_y,
-                            const float* bn_mean, const float* bn_invstd, cudaStream_t stream) {
+                            const float* bn_mean, const float* bn_invstd, cudaStream_t stream,
+                            int taps = 9) {
   if (N <= 0 || H <= 0 || W <= 0) return FPB200_ERR_SHAPE;
-  if (Cin % 16 != 0 || Cout % 64 != 0 || Cout > 2048) return FPB200_ERR_SHAPE;
+  if (taps == 1 && (Cin % 64 != 0 || bn_y != nullptr)) return FPB200_ERR_SHAPE;
+  if (Cin % 16 != 0 || Cout % 64 != 0 || Cout > 4096) return FPB200_ERR_SHAPE;
   if ((ldx % 8) != 0 || (ldy % 8) != 0 || ldx < Cin || ldy < Cout) return FPB200_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
       (reinterpret_cast<uintptr_t>(w_packed) & 15))
@@ -474,9 +481,10 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
   p.stat_partials = stat_partials;
 
   CUtensorMap tmA, tmB, tmY;
-  int rc = make_tmap_act(&tmA, x, N, H, W, Cin, ldx, KCH, kBox, kBox);
+  const int box = kPatch + (taps == 9 ? 2 : 0);
+  int rc = make_tmap_act(&tmA, x, N, H, W, Cin, ldx, KCH, box, box);
   if (rc != FPB200_OK) return rc;
-  rc = make_tmap_mat(&tmB, w_packed, Cout, 9L * Cin, KCH, BN);
+  rc = make_tmap_mat(&tmB, w_packed, Cout, (long)taps * Cin, KCH, BN);
   if (rc != FPB200_OK) return rc;
   rc = make_tmap_act(&tmY, y, N, H, W, Cout, ldy, 64, 8, 4);  // epilogue store box: 8 px x 4 rows x 64 ch
   if (rc != FPB200_OK) return rc;
@@ -490,14 +498,16 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
                         stream) != cudaSuccess)
       return check_launch("conv3x3 stat memset");
   }
-#define FP_HALO_CASE(bn, kch) \
-  if (BN == bn && KCH == kch) return launch_halo<bn, kch>(tmA, tmB, tmY, tmYL, p, stream);
-  FP_HALO_CASE(128, 64)
-  FP_HALO_CASE(64, 64)
-  FP_HALO_CASE(128, 32)
-  FP_HALO_CASE(64, 32)
-  FP_HALO_CASE(128, 16)
-  FP_HALO_CASE(64, 16)
+#define FP_HALO_CASE(bn, kch, tp) \
+  if (BN == bn && KCH == kch && taps == tp) return launch_halo<bn, kch, tp>(tmA, tmB, tmY, tmYL, p, stream);
+  FP_HALO_CASE(128, 64, 9)
+  FP_HALO_CASE(64, 64, 9)
+  FP_HALO_CASE(128, 32, 9)
+  FP_HALO_CASE(64, 32, 9)
+  FP_HALO_CASE(128, 16, 9)
+  FP_HALO_CASE(64, 16, 9)
+  FP_HALO_CASE(128, 64, 1)
+  FP_HALO_CASE(64, 64, 1)
 #undef FP_HALO_CASE
   return FPB200_ERR_SHAPE;
 }
@@ -536,6 +546,17 @@ int fpb200_conv3x3_dgrad_bf16_nhwc(const void* dy, long lddy, const void* w_pack
                               bn_y ? bn_scale : nullptr, bn_y ? bn_shift : nullptr, 0,
                               bn_y ? bn_partials : nullptr, bn_y, ld_bn_y, bn_mean, bn_invstd,
                               static_cast<cudaStream_t>(stream));
+}
+
+/* pointwise (1x1) convolution: forward with w_packed = [Cout][Cin], data gradient with the
+ * transposed packing [Cin][Cout] (then "Cin"/"Cout" swap roles, as for the 3x3 dgrad). */
+int fpb200_conv1x1_bf16_nhwc(const void* x, long ldx, const void* w_packed, void* y, long ldy, int N,
+                             int H, int W, int Cin, int Cout, const float* scale, const float* shift,
+                             int relu, void* stream) {
+  if ((scale == nullptr) != (shift == nullptr)) return FPB200_ERR_SHAPE;
+  return fp::conv3x3_dispatch(x, ldx, w_packed, y, ldy, N, H, W, Cin, Cout, scale, shift, relu,
+                              nullptr, nullptr, 0, nullptr, nullptr,
+                              static_cast<cudaStream_t>(stream), 1);
 }
 
 }  // extern "C"

@@ -27,6 +27,8 @@
 //                  A = dy box with halo (18 x 6 px); two taps are stacked on M (2 x 64 co) by
 //                  pointing the descriptor's second 64-row block (LBO) at the other tap's
 //                  offset inside the same box; B = x, unshifted.  5 pairs cover the 9 taps.
+//   MODE_POINTWISE (1x1 convolution, the late-fusion concat_convs): no halo, one tap:
+//                  A = 128 output channels of dy, B = NB blocks of 64 input channels of x.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -46,24 +48,26 @@ struct WgradParams {
   int items_ci;     // number of ci groups (item = co_grp * items_ci * items_r + ci_grp * items_r + r)
   int items_r;      // 3 in MODE_X_SHIFT, 1 in MODE_DY_SHIFT
   int Cout, Cin;    // Cin = padded input channels (layout of the partials)
-  float* ws;        // [ksplit][Cout][9][Cin]
+  int taps;         // 9 (3x3) or 1 (pointwise)
+  float* ws;        // [ksplit][Cout][taps][Cin]
 };
 
 template <int MODE, int NBW, int NB>
 struct WgCfg {
   // A = dy.  mode 0: two [64 px][64 co] blocks; mode 1: one haloed box 18 x 6 px (padded slot)
-  static constexpr int kABlock = MODE == 0 ? kWgBK * 128 : kWgBoxW * (kWgTH + 2) * 128;
-  static constexpr int kABytes = MODE == 0 ? 2 * kABlock : kABlock;          // TMA bytes
-  static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024 + (MODE == 0 ? 0 : 1024);
-  // B = x.  mode 0: NB blocks of one filter row with halo [18 x 4 px][64 ci]; mode 1: [64 px][NBW]
+  static constexpr int kABlock = MODE != 1 ? kWgBK * 128 : kWgBoxW * (kWgTH + 2) * 128;
+  static constexpr int kABytes = MODE != 1 ? 2 * kABlock : kABlock;          // TMA bytes
+  static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024 + (MODE != 1 ? 0 : 1024);
+  // B = x.  mode 0: NB blocks of one filter row with halo [18 x 4 px][64 ci]; mode 1: [64 px][NBW];
+  // mode 2: NB blocks [64 px][64 ci]
   static constexpr int kBBlock = MODE == 0 ? kWgBoxW * kWgTH * 128 : kWgBK * NBW * 2;
-  static constexpr int kBBytes = MODE == 0 ? NB * kBBlock : kBBlock;
+  static constexpr int kBBytes = MODE != 1 ? NB * kBBlock : kBBlock;
   static constexpr int kBSlot = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kASlot + kBSlot;
   static constexpr int kTxBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kGroups = MODE == 0 ? 3 : 5;
+  static constexpr int kGroups = MODE == 0 ? 3 : (MODE == 1 ? 5 : 1);
   static constexpr int kN = NBW * NB;                     // UMMA N per group
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
@@ -82,7 +86,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   using Cfg = WgCfg<MODE, NBW, NB>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kIdesc = make_idesc_bf16(128, Cfg::kN, 1, 1);
-  constexpr uint32_t kBRow = MODE == 0 ? 128 : NBW * 2;   // bytes per pixel row of B
+  constexpr uint32_t kBRow = MODE != 1 ? 128 : NBW * 2;   // bytes per pixel row of B
   constexpr uint32_t kBSwz = kBRow;
   constexpr uint32_t kBSBO = 8 * kBRow;
 
@@ -104,7 +108,10 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   const int r_idx = item % p.items_r;
   const int ci_grp = (item / p.items_r) % p.items_ci;
   const int co_grp = item / (p.items_r * p.items_ci);
-  const int co0 = co_grp * (MODE == 0 ? 128 : 64);
+  const int co0 = co_grp * (MODE != 1 ? 128 : 64);
+  // second 64-channel block of A; a 64-channel pointwise layer re-reads the first block (its
+  // duplicate accumulator rows are discarded)
+  const int co1 = (MODE == 2 && co0 + 64 >= p.Cout) ? co0 : co0 + 64;
   const int ci0 = ci_grp * Cfg::kN;
   const int t_begin = (int)(((long)p.num_pix_tiles * split) / p.ksplit);
   const int t_end = (int)(((long)p.num_pix_tiles * (split + 1)) / p.ksplit);
@@ -143,11 +150,17 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         mbar_arrive_expect_tx(full_bar(stage), Cfg::kTxBytes);
         if (MODE == 0) {
           tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0, h0, img);
-          tma_load_4d(sa + Cfg::kABlock, &tmDY, full_bar(stage), co0 + 64, w0, h0, img);
+          tma_load_4d(sa + Cfg::kABlock, &tmDY, full_bar(stage), co1, w0, h0, img);
 #pragma unroll
           for (int b = 0; b < NB; ++b)
             tma_load_4d(sb + b * Cfg::kBBlock, &tmX, full_bar(stage), ci0 + b * 64, w0 - 1,
                         h0 + r_idx - 1, img);
+        } else if (MODE == 2) {
+          tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0, h0, img);
+          tma_load_4d(sa + Cfg::kABlock, &tmDY, full_bar(stage), co1, w0, h0, img);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            tma_load_4d(sb + b * Cfg::kBBlock, &tmX, full_bar(stage), ci0 + b * 64, w0, h0, img);
         } else {
           tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0 - 1, h0 - 1, img);
           tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0, h0, img);
@@ -182,6 +195,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
               // B: x row k of the haloed filter-row box, shifted by tap s = g pixels
               b_lo = (b_addr16 + (((k * kWgBoxW + g) * 128) >> 4)) |
                      ((uint32_t(Cfg::kBBlock) >> 4) << 16);
+            } else if (MODE == 2) {
+              a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
+              b_lo = (b_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kBBlock) >> 4) << 16);
             } else {
               // A: haloed dy box; first M block at the pair's first tap, second block LBO further
               a_lo = (a_addr16 + (((k * kWgBoxW + wg_pair_offset(g)) * 128) >> 4)) |
@@ -204,18 +220,22 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const bool have = t_end > t_begin;
-    float* ws = p.ws + (size_t)split * p.Cout * 9 * p.Cin;
+    float* ws = p.ws + (size_t)split * p.Cout * p.taps * p.Cin;
 #pragma unroll
     for (int g = 0; g < Cfg::kGroups; ++g) {
       int co, tap;
       if (MODE == 0) {
         co = co0 + row;
         tap = r_idx * 3 + g;
+      } else if (MODE == 2) {
+        co = co0 + row;
+        tap = co < p.Cout ? 0 : -1;
+        if (tap < 0) co = 0;
       } else {
         co = co0 + (row & 63);
         tap = (row < 64) ? 8 - 2 * g : 7 - 2 * g;   // group 4: tap 0 and a discarded half (-1)
       }
-      float* dst = ws + ((size_t)co * 9 + (tap < 0 ? 0 : tap)) * p.Cin + ci0;
+      float* dst = ws + ((size_t)co * p.taps + (tap < 0 ? 0 : tap)) * p.Cin + ci0;
 #pragma unroll
       for (int c = 0; c < Cfg::kN / 16; ++c) {
         uint32_t r[16];
@@ -247,17 +267,17 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 
 // dw[co][ci][tap] = sum_split ws[split][co][tap][ci_pad]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit,
-                                    int Cout, int Cin, int cin_real) {
-  const long total = (long)Cout * 9 * Cin;
+                                    int Cout, int Cin, int cin_real, int taps) {
+  const long total = (long)Cout * taps * Cin;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
     const int ci = i % Cin;
-    const int tap = (i / Cin) % 9;
-    const int co = i / (9L * Cin);
+    const int tap = (i / Cin) % taps;
+    const int co = i / ((long)taps * Cin);
     if (ci >= cin_real) continue;
     float acc = 0.f;
     for (int s = 0; s < ksplit; ++s) acc += ws[(size_t)s * total + i];
-    dw[((long)co * cin_real + ci) * 9 + tap] = acc;
+    dw[((long)co * cin_real + ci) * taps + tap] = acc;
   }
 }
 
@@ -267,9 +287,15 @@ struct WgPlan {
   int tiles_w, tiles_h, num_pix_tiles;
 };
 
-static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl) {
+static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl, int taps = 9) {
   if (Cout % 64 != 0 || Cin % 16 != 0) return FPB200_ERR_SHAPE;
-  if (Cout % 128 == 0 && Cin % 64 == 0) {
+  if (taps == 1) {
+    if (Cin % 64 != 0) return FPB200_ERR_SHAPE;
+    pl->mode = 2; pl->nbw = 64; pl->nb = (Cin % 128 == 0) ? 2 : 1;
+    pl->items_r = 1;
+    pl->items_ci = Cin / (64 * pl->nb);
+    pl->n_items = ((Cout + 127) / 128) * pl->items_ci;
+  } else if (Cout % 128 == 0 && Cin % 64 == 0) {
     pl->mode = 0; pl->nbw = 64; pl->nb = (Cin % 128 == 0) ? 2 : 1;
     pl->items_r = 3;
     pl->items_ci = Cin / (64 * pl->nb);
@@ -356,7 +382,7 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.num_pix_tiles = pl.num_pix_tiles;
   p.ksplit = pl.ksplit; p.n_items = pl.n_items; p.items_ci = pl.items_ci; p.items_r = pl.items_r;
-  p.Cout = Cout; p.Cin = Cin;
+  p.Cout = Cout; p.Cin = Cin; p.taps = 9;
   p.ws = reinterpret_cast<float*>(workspace);
   if (pl.mode == 0 && pl.nb == 2) rc = launch_wgrad<0, 64, 2>(tmDY, tmX, p, stream);
   else if (pl.mode == 0) rc = launch_wgrad<0, 64, 1>(tmDY, tmX, p, stream);
@@ -367,7 +393,46 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
   const long total = (long)Cout * 9 * Cin;
   long g = (total + 255) / 256;
   if (g > 148L * 8) g = 148L * 8;
-  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(p.ws, dw_oihw, pl.ksplit, Cout, Cin, cin_real);
+  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(p.ws, dw_oihw, pl.ksplit, Cout, Cin, cin_real, 9);
+  return check_launch("wgrad_reduce");
+}
+
+long fpb200_conv1x1_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout) {
+  WgPlan pl;
+  if (plan_wgrad(N, H, W, Cin, Cout, &pl, 1) != FPB200_OK) return -1;
+  return (long)pl.ksplit * Cout * Cin * (long)sizeof(float);
+}
+
+int fpb200_conv1x1_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long lddy, float* dw_oi,
+                                   void* workspace, int N, int H, int W, int Cin, int Cout,
+                                   void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  WgPlan pl;
+  int rc = plan_wgrad(N, H, W, Cin, Cout, &pl, 1);
+  if (rc != FPB200_OK) return rc;
+  if (ldx % 8 != 0 || lddy % 8 != 0 || ldx < Cin || lddy < Cout) return FPB200_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return FPB200_ERR_ALIGN;
+  CUtensorMap tmDY, tmX;
+  rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgTW, kWgTH);
+  if (rc != FPB200_OK) return rc;
+  rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, 64, kWgTW, kWgTH);
+  if (rc != FPB200_OK) return rc;
+  WgradParams p;
+  p.N = N; p.H = H; p.W = W;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
+  p.num_pix_tiles = pl.num_pix_tiles;
+  p.ksplit = pl.ksplit; p.n_items = pl.n_items; p.items_ci = pl.items_ci; p.items_r = pl.items_r;
+  p.Cout = Cout; p.Cin = Cin; p.taps = 1;
+  p.ws = reinterpret_cast<float*>(workspace);
+  rc = pl.nb == 2 ? launch_wgrad<2, 64, 2>(tmDY, tmX, p, stream)
+                  : launch_wgrad<2, 64, 1>(tmDY, tmX, p, stream);
+  if (rc != FPB200_OK) return rc;
+  const long total = (long)Cout * Cin;
+  long g = (total + 255) / 256;
+  if (g > 148L * 8) g = 148L * 8;
+  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(p.ws, dw_oi, pl.ksplit, Cout, Cin, Cin, 1);
   return check_launch("wgrad_reduce");
 }
 

@@ -167,6 +167,94 @@ def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, workspace
 
 
 # ------------------------------------------------------------------------------------------
+# pointwise (1x1) convolution and the feature-level seams (late fusion, encode/decode API)
+def repack_1x1(w: torch.Tensor, transpose: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [Cout, Cin, 1, 1] -> bf16 [Cout, Cin] (forward) or [Cin, Cout] (data gradient)."""
+    _require_cuda(w)
+    cout, cin = w.shape[0], w.shape[1]
+    if out is None:
+        out = torch.empty((cin, cout) if transpose else (cout, cin), dtype=torch.bfloat16, device=w.device)
+    st = _lib().fpb200_repack_weights_1x1(w.detach().contiguous().data_ptr(), out.data_ptr(), cout, cin,
+                                          int(transpose), _stream())
+    capi.check(st, "repack_weights_1x1", Cout=cout, Cin=cin, transpose=transpose)
+    return out
+
+
+def conv1x1(x: torch.Tensor, w_packed: torch.Tensor, y: torch.Tensor,
+            scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+            relu: bool = False) -> None:
+    """y = x . w_packed^T per pixel (w_packed bf16 [Cout_gemm, Cin_gemm]), optional affine."""
+    _require_cuda(x, w_packed, y)
+    xp, ldx = nhwc_view(x)
+    yp, ldy = nhwc_view(y)
+    n, h, w, cin = x.shape
+    cout = y.shape[3]
+    if tuple(w_packed.shape) != (cout, cin):
+        raise RuntimeError(f"conv1x1: packed weight {tuple(w_packed.shape)} != ({cout}, {cin})")
+    st = _lib().fpb200_conv1x1_bf16_nhwc(xp, ldx, w_packed.data_ptr(), yp, ldy, n, h, w, cin, cout,
+                                         _ptr(scale), _ptr(shift), int(relu), _stream())
+    capi.check(st, "conv1x1_bf16_nhwc", N=n, H=h, W=w, Cin=cin, Cout=cout)
+
+
+def conv1x1_wgrad_workspace_bytes(n: int, h: int, w: int, cin: int, cout: int) -> int:
+    b = _lib().fpb200_conv1x1_wgrad_workspace_bytes(n, h, w, cin, cout)
+    if b < 0:
+        raise RuntimeError(f"conv1x1_wgrad: unsupported shape Cin={cin} Cout={cout}")
+    return b
+
+
+def conv1x1_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, workspace: torch.Tensor) -> None:
+    """dw (fp32 [Cout, Cin, 1, 1] or [Cout, Cin], contiguous) is overwritten."""
+    _require_cuda(x, dy, dw, workspace)
+    xp, ldx = nhwc_view(x)
+    dyp, lddy = nhwc_view(dy)
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    need = conv1x1_wgrad_workspace_bytes(n, h, w, cin, cout)
+    if workspace.numel() * workspace.element_size() < need or not dw.is_contiguous() \
+            or dw.numel() != cout * cin:
+        raise RuntimeError("conv1x1_wgrad: workspace too small or dw not a contiguous [Cout, Cin]")
+    st = _lib().fpb200_conv1x1_wgrad_bf16_nhwc(xp, ldx, dyp, lddy, dw.data_ptr(), workspace.data_ptr(),
+                                               n, h, w, cin, cout, _stream())
+    capi.check(st, "conv1x1_wgrad_bf16_nhwc", N=n, H=h, W=w, Cin=cin, Cout=cout)
+
+
+def channel_sum(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[c] (fp32) = sum over pixels of the NHWC bf16 view x."""
+    _require_cuda(x, out)
+    xp, ld = nhwc_view(x)
+    n, h, w, c = x.shape
+    rows = _lib().fpb200_channel_sum_rows()
+    partials = torch.empty((rows, c), dtype=torch.float32, device=x.device)
+    st = _lib().fpb200_channel_sum_bf16_nhwc(xp, ld, partials.data_ptr(), out.data_ptr(), n * h * w, c,
+                                             _stream())
+    capi.check(st, "channel_sum_bf16_nhwc", N=n, H=h, W=w, C=c)
+
+
+def nchw_f32_to_nhwc_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """fp32 NCHW tensor -> bf16 NHWC view `dst` ([N,H,W,C], may be a channel slice)."""
+    _require_cuda(src, dst)
+    src = src.contiguous() if src.dtype == torch.float32 else src.float().contiguous()
+    dp, ld = nhwc_view(dst)
+    n, c, h, w = src.shape
+    if tuple(dst.shape) != (n, h, w, c):
+        raise RuntimeError(f"nchw_f32_to_nhwc_bf16: {tuple(src.shape)} vs view {tuple(dst.shape)}")
+    st = _lib().fpb200_nchw_f32_to_nhwc_bf16(src.data_ptr(), dp, ld, n, c, h, w, _stream())
+    capi.check(st, "nchw_f32_to_nhwc_bf16", N=n, C=c, H=h, W=w)
+
+
+def nhwc_bf16_to_nchw_f32(src: torch.Tensor) -> torch.Tensor:
+    """bf16 NHWC view -> fresh fp32 NCHW tensor."""
+    _require_cuda(src)
+    sp, ld = nhwc_view(src)
+    n, h, w, c = src.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
+    st = _lib().fpb200_nhwc_bf16_to_nchw_f32(sp, ld, out.data_ptr(), n, c, h, w, _stream())
+    capi.check(st, "nhwc_bf16_to_nchw_f32", N=n, C=c, H=h, W=w)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 def bn_stats_finalize(partials, count, gamma, beta, conv_bias, eps, momentum, running_mean,
                       running_var, scale, shift, save_mean, save_invstd) -> None:
     c = gamma.numel()

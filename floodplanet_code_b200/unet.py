@@ -16,7 +16,8 @@ from typing import Sequence
 import torch
 import torch.nn as nn
 
-from .engine import UNetEngine
+from . import ops
+from .engine import DecoderEngine, EncoderEngine, UNetEngine
 
 
 class _ContainerOnly(nn.Module):
@@ -119,6 +120,8 @@ class UNet(nn.Module):
         self.outc = OutConv(64, n_classes)
 
         self._engine = UNetEngine(n_channels, n_classes)
+        self._enc_engine = None   # built on first encode() / decode()
+        self._dec_engine = None
 
     # -- the hot path -----------------------------------------------------------------------
     def forward(self, x):
@@ -146,18 +149,176 @@ class UNet(nn.Module):
                                        training=self.training, save=False)
         return logits
 
-    # -- reference API kept for completeness (late fusion only; out of the hot path) ----------
+    # -- feature-level API (reference unet.py:113-131; used by late fusion) ---------------------
     def encode(self, x):
-        raise NotImplementedError(
-            "UNet.encode/decode are only used by the late-fusion model (lf_model.py), which is "
-            "outside the B200 hot-path scope (SURVEY.md section 8f)")
+        """[x1, x2, x3, x4, x5] as fp32 NCHW tensors (unet.py:113-120)."""
+        if self._enc_engine is None:
+            self._enc_engine = EncoderEngine(self.n_channels)
+        return _run_encoder_module(self, self._enc_engine, [x])
 
     def decode(self, feats):
-        raise NotImplementedError(
-            "UNet.encode/decode are only used by the late-fusion model (lf_model.py), which is "
-            "outside the B200 hot-path scope (SURVEY.md section 8f)")
+        """logits from the five features (unet.py:122-131)."""
+        if self._dec_engine is None:
+            self._dec_engine = DecoderEngine(self.n_classes)
+        return _run_decoder_module(self, self._dec_engine, feats)
 
     @property
     def kernel_launches(self) -> int:
         """CUDA kernels launched by the most recent forward or backward pass."""
         return self._engine.launches
+
+
+# ---------------------------------------------------------------------------------------------
+# encoder / decoder halves as stand-alone autograd nodes (fp32 NCHW feature lists at the seam)
+# ---------------------------------------------------------------------------------------------
+def _check_cuda_nchw(tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(
+                "floodplanet_b200 runs on CUDA (sm_100a) only; got a "
+                f"{t.device.type} tensor and there is no CPU fallback")
+        if t.dim() != 4:
+            raise RuntimeError(f"expected NCHW input, got shape {tuple(t.shape)}")
+
+
+class _EncoderFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, module, engine, n_images, *tensors):
+        images, plist = tensors[:n_images], tensors[n_images:]
+        params = dict(zip(engine.names, plist))
+        feats, st = engine.forward(images, params, dict(module.named_buffers()), training=True, save=True)
+        ctx.engine, ctx.state, ctx.n_images = engine, st, n_images
+        ctx.save_for_backward(*plist)
+        return tuple(ops.nhwc_bf16_to_nchw_f32(f) for f in feats)
+
+    @staticmethod
+    def backward(ctx, *d_feats):
+        engine = ctx.engine
+        if ctx.state is None:
+            raise RuntimeError("floodplanet_b200: backward called twice on the same encoder forward")
+        st = ctx.state
+        params = dict(zip(engine.names, ctx.saved_tensors))
+        d_nhwc = []
+        for l, g in enumerate(d_feats):
+            hh, ww = st.sizes[l]
+            c = (64, 128, 256, 512, 512)[l]
+            buf = torch.zeros((st.n, hh, ww, c), dtype=torch.bfloat16, device=ctx.saved_tensors[0].device)
+            if g is not None:
+                ops.nchw_f32_to_nhwc_bf16(g, buf)
+            d_nhwc.append(buf)
+        grads, _ = engine.backward(st, d_nhwc, params)
+        ctx.state = None
+        return (None, None, None) + (None,) * ctx.n_images + tuple(grads[n] for n in engine.names)
+
+
+class _DecoderFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, module, engine, *tensors):
+        feats, plist = tensors[:5], tensors[5:]
+        params = dict(zip(engine.names, plist))
+        logits, st = engine.forward(feats, params, dict(module.named_buffers()), training=True, save=True)
+        ctx.engine, ctx.state = engine, st
+        ctx.save_for_backward(*plist)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        engine = ctx.engine
+        if ctx.state is None:
+            raise RuntimeError("floodplanet_b200: backward called twice on the same decoder forward")
+        params = dict(zip(engine.names, ctx.saved_tensors))
+        grads, _, d_feats = engine.backward(ctx.state, dlogits, params)
+        ctx.state = None
+        d_nchw = tuple(ops.nhwc_bf16_to_nchw_f32(g) if ctx.needs_input_grad[2 + l] else None
+                       for l, g in enumerate(d_feats))
+        return (None, None) + d_nchw + tuple(grads[n] for n in engine.names)
+
+
+def _run_encoder_module(module: nn.Module, engine: EncoderEngine, images):
+    images = list(images)
+    _check_cuda_nchw(images)
+    params = dict(module.named_parameters())
+    plist = [params[n] for n in engine.names]
+    if torch.is_grad_enabled() and module.training and any(p.requires_grad for p in plist):
+        return list(_EncoderFunction.apply(module, engine, len(images), *images, *plist))
+    with torch.no_grad():
+        feats, _ = engine.forward(images, params, dict(module.named_buffers()),
+                                  training=module.training, save=False)
+        return [ops.nhwc_bf16_to_nchw_f32(f) for f in feats]
+
+
+def _run_decoder_module(module: nn.Module, engine: DecoderEngine, feats, head: bool = True):
+    feats = list(feats)
+    _check_cuda_nchw(feats)
+    params = dict(module.named_parameters())
+    plist = [params[n] for n in engine.names]
+    needs_grad = torch.is_grad_enabled() and module.training and (
+        any(p.requires_grad for p in plist) or any(f.requires_grad for f in feats))
+    if needs_grad:
+        if not head:
+            raise RuntimeError("floodplanet_b200: get_output_feats is inference-only on this path "
+                               "(no caller in the reference differentiates through it)")
+        return _DecoderFunction.apply(module, engine, *feats, *plist)
+    with torch.no_grad():
+        out, _ = engine.forward(feats, params, dict(module.named_buffers()), training=module.training,
+                                save=False, head=head)
+        return out if head else ops.nhwc_bf16_to_nchw_f32(out)
+
+
+class UNetEncoder(nn.Module):
+    """``UNetEncoder(n_channels, bilinear=True, base_feat_channels=64)`` -- reference
+    unet.py:134-159.  forward(x) -> [x1..x5] (fp32 NCHW)."""
+
+    def __init__(self, n_channels, bilinear=True, base_feat_channels=64):
+        super(UNetEncoder, self).__init__()
+        if base_feat_channels != 64 or not bilinear:
+            raise NotImplementedError("the B200 path builds the widths the reference instantiates "
+                                      "(base_feat_channels=64, bilinear=True; lf_model.py:36-38)")
+        self.n_channels = n_channels
+        self.bilinear = bilinear
+        bfc = base_feat_channels
+        self.base_feat_channels = base_feat_channels
+
+        self.inc = DoubleConv(n_channels, bfc)
+        self.down1 = Down(bfc, bfc * 2)
+        self.down2 = Down(bfc * 2, bfc * 4)
+        self.down3 = Down(bfc * 4, bfc * 8)
+        factor = 2 if bilinear else 1
+        self.down4 = Down(bfc * 8, (bfc * 16) // factor)
+        self._engine = EncoderEngine(n_channels)
+
+    def forward(self, x):
+        return _run_encoder_module(self, self._engine, [x])
+
+
+class UNetDecoder(nn.Module):
+    """``UNetDecoder(n_classes, bilinear=True, channel_factor=1, base_feat_channels=64)`` --
+    reference unet.py:162-191."""
+
+    def __init__(self, n_classes, bilinear=True, channel_factor=1, base_feat_channels=64):
+        super(UNetDecoder, self).__init__()
+        if base_feat_channels != 64 or not bilinear or channel_factor != 1:
+            raise NotImplementedError("the B200 path builds the widths the reference instantiates "
+                                      "(channel_factor=1, base_feat_channels=64, bilinear=True; "
+                                      "lf_model.py:40)")
+        self.n_classes = n_classes
+        self.bilinear = bilinear
+        cf = channel_factor
+        bfc = base_feat_channels
+        self.base_feat_channels = base_feat_channels
+
+        factor = 2 if bilinear else 1
+        self.up1 = Up((bfc * 16) * cf, (bfc * 8) // factor, bilinear)
+        self.up2 = Up((bfc * 8) // factor * (cf + 1), (bfc * 4) // factor, bilinear)
+        self.up3 = Up((bfc * 4) // factor * (cf + 1), (bfc * 2) // factor, bilinear)
+        self.up4 = Up((bfc * 2) // factor * (cf + 1), bfc, bilinear)
+        self.outc = OutConv(bfc, n_classes)
+        self._engine = DecoderEngine(n_classes)
+
+    def forward(self, feats):
+        return _run_decoder_module(self, self._engine, feats)
+
+    def get_output_feats(self, feats):
+        return _run_decoder_module(self, self._engine, feats, head=False)

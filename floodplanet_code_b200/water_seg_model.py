@@ -205,6 +205,8 @@ MODELS = {
     'ms_model': WaterSegmentationModel,
     'ef_model': EarlyFusionModel,
 }
+# 'lf_model' is registered by lf_model.py (imported at the bottom of this module: it subclasses
+# WaterSegmentationModel, so it has to come after the class definitions)
 
 
 def build_model(model_name, input_channels, n_classes, lr, log_image_iter, to_rgb_fcn, ignore_index,
@@ -224,12 +226,21 @@ def install_into_reference() -> None:
     classes without editing them: patch ``st_water_seg.models`` after it is imported."""
     import importlib
     ref = importlib.import_module("st_water_seg.models")
+    from .unet import UNetDecoder, UNetEncoder
+    LateFusionModel = MODELS['lf_model']
     ref.MODELS['ms_model'] = WaterSegmentationModel
     ref.MODELS['ef_model'] = EarlyFusionModel
+    ref.MODELS['lf_model'] = LateFusionModel
     for modname, cls in (("st_water_seg.models.unet", UNet),
+                         ("st_water_seg.models.unet", UNetEncoder),
+                         ("st_water_seg.models.unet", UNetDecoder),
                          ("st_water_seg.models.water_seg_model", WaterSegmentationModel),
-                         ("st_water_seg.models.ef_model", EarlyFusionModel)):
+                         ("st_water_seg.models.ef_model", EarlyFusionModel),
+                         ("st_water_seg.models.lf_model", LateFusionModel)):
         try:
             setattr(importlib.import_module(modname), cls.__name__, cls)
         except Exception:
             pass
+
+
+from . import lf_model as _lf_model  # noqa: E402,F401  (registers MODELS['lf_model'])

@@ -251,6 +251,47 @@ int fpb200_canvas_to_mask_u8(const float* canvas, const float* weight, uint8_t* 
                              int n_classes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Feature-level seams: encoder/decoder API and late fusion
+ *   models/unet.py:113-131 (UNet.encode / UNet.decode), :134-191 (UNetEncoder / UNetDecoder),
+ *   models/lf_model.py:29-92 (per-modality encoders, torch.concat of the five feature levels,
+ *   concat_convs = nn.Conv2d(fs*k, fs, 1, 1), decoder) and their autograd
+ * ---------------------------------------------------------------------------------------- */
+
+/* Feature-map layout/cast at the encode()/decode() boundary (callers exchange fp32 NCHW lists):
+ *   fp32 [N][C][H][W]  ->  bf16 NHWC view (pitch ld, channels [0,C)), and back.  C % 8 == 0. */
+int fpb200_nchw_f32_to_nhwc_bf16(const float* src, void* dst, long ld, int N, int C, int H, int W,
+                                 void* stream);
+int fpb200_nhwc_bf16_to_nchw_f32(const void* src, long ld, float* dst, int N, int C, int H, int W,
+                                 void* stream);
+
+/* 1x1 conv weight repack: fp32 [Cout][Cin] -> bf16 [Cout][Cin] (transpose == 0, forward operand)
+ * or bf16 [Cin][Cout] (transpose != 0, data-gradient operand).  lf_model.py:44-45. */
+int fpb200_repack_weights_1x1(const float* w_oi, void* w_packed, int Cout, int Cin, int transpose,
+                              void* stream);
+
+/* y = conv1x1(x, w) on the tensor cores (same TMA/tcgen05 pipeline as the 3x3 kernel with a
+ * halo-free box and one tap), bf16 NHWC views, fp32 accumulate.  Cin % 64 == 0, Cout % 64 == 0.
+ *   scale/shift (both or neither, [Cout], Cout <= 512): y = acc*scale+shift (+ReLU); the
+ *   late-fusion forward passes scale = 1, shift = bias (lf_model.py:88 `concat_conv(img_feat)`).
+ * The data gradient is the same call with the transposed packing and Cin/Cout swapped. */
+int fpb200_conv1x1_bf16_nhwc(const void* x, long ldx, const void* w_packed, void* y, long ldy, int N,
+                             int H, int W, int Cin, int Cout, const float* scale, const float* shift,
+                             int relu, void* stream);
+
+/* dW[co][ci] = sum_pixels dy[p][co] * x[p][ci]  (split-K on the tensor cores + deterministic
+ * reduction, as for the 3x3 weight gradient); dw_oi fp32 [Cout][Cin] is overwritten. */
+long fpb200_conv1x1_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+int fpb200_conv1x1_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long lddy, float* dw_oi,
+                                   void* workspace, int N, int H, int W, int Cin, int Cout,
+                                   void* stream);
+
+/* out[c] = sum_pixels x[p][c]: bias gradient of a pointwise conv.  partials: fp32
+ * [fpb200_channel_sum_rows()][C] workspace.  C/8 must divide 256 (C = 64 ... 512 here). */
+int fpb200_channel_sum_rows(void);
+int fpb200_channel_sum_bf16_nhwc(const void* x, long ld, float* partials, float* out,
+                                 long num_pixels, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimiser (water_seg_model.py:198-205, optim.Adam defaults) and misc
  * ---------------------------------------------------------------------------------------- */
 

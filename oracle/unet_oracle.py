@@ -16,6 +16,8 @@ installed torch 2.11).  Each function cites the reference lines it restates:
   1x1 head                st_water_seg/models/unet.py:70-77     (OutConv)
   wiring                  st_water_seg/models/unet.py:80-111    (UNet.__init__/forward)
   early-fusion concat     st_water_seg/models/ef_model.py:24-47
+  encode / decode halves  st_water_seg/models/unet.py:113-131, 134-191 (UNetEncoder / UNetDecoder)
+  late fusion             st_water_seg/models/lf_model.py:29-92
   loss / NaN guard / pred st_water_seg/models/water_seg_model.py:40,98-107
   Adam                    st_water_seg/models/water_seg_model.py:198-205
 
@@ -150,22 +152,126 @@ def unet_forward_bf16_emulated(sd: Dict[str, torch.Tensor], x: torch.Tensor, tra
         _EMULATE_BF16 = False
 
 
+def unet_encode(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True, prefix: str = ""):
+    """unet.py:113-120 (UNet.encode) / :150-159 (UNetEncoder.forward) -> [x1..x5]."""
+    x1 = _double_conv(x, sd, f"{prefix}inc.double_conv", training)
+    x2 = _double_conv(F.max_pool2d(x1, 2), sd, f"{prefix}down1.maxpool_conv.1.double_conv", training)
+    x3 = _double_conv(F.max_pool2d(x2, 2), sd, f"{prefix}down2.maxpool_conv.1.double_conv", training)
+    x4 = _double_conv(F.max_pool2d(x3, 2), sd, f"{prefix}down3.maxpool_conv.1.double_conv", training)
+    x5 = _double_conv(F.max_pool2d(x4, 2), sd, f"{prefix}down4.maxpool_conv.1.double_conv", training)
+    return [x1, x2, x3, x4, x5]
+
+
+def unet_decode(sd: Dict[str, torch.Tensor], feats: Sequence[torch.Tensor], training: bool = True,
+                prefix: str = "", head: bool = True):
+    """unet.py:122-131 (UNet.decode) / :176-191 (UNetDecoder.forward, get_output_feats)."""
+    x1, x2, x3, x4, x5 = feats
+    u = _up(x5, x4, sd, f"{prefix}up1.conv.double_conv", training)
+    u = _up(u, x3, sd, f"{prefix}up2.conv.double_conv", training)
+    u = _up(u, x2, sd, f"{prefix}up3.conv.double_conv", training)
+    u = _up(u, x1, sd, f"{prefix}up4.conv.double_conv", training)
+    if not head:
+        return u
+    return F.conv2d(u, sd[f"{prefix}outc.conv.weight"], sd[f"{prefix}outc.conv.bias"])
+
+
 def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True,
                  return_features: bool = False):
     """unet.py:100-111.  ``sd`` BN buffers are updated in place when ``training``."""
-    x1 = _double_conv(x, sd, "inc.double_conv", training)
-    x2 = _double_conv(F.max_pool2d(x1, 2), sd, "down1.maxpool_conv.1.double_conv", training)
-    x3 = _double_conv(F.max_pool2d(x2, 2), sd, "down2.maxpool_conv.1.double_conv", training)
-    x4 = _double_conv(F.max_pool2d(x3, 2), sd, "down3.maxpool_conv.1.double_conv", training)
-    x5 = _double_conv(F.max_pool2d(x4, 2), sd, "down4.maxpool_conv.1.double_conv", training)
-    u = _up(x5, x4, sd, "up1.conv.double_conv", training)
-    u = _up(u, x3, sd, "up2.conv.double_conv", training)
-    u = _up(u, x2, sd, "up3.conv.double_conv", training)
-    u = _up(u, x1, sd, "up4.conv.double_conv", training)
-    logits = F.conv2d(u, sd["outc.conv.weight"], sd["outc.conv.bias"])
+    feats = unet_encode(sd, x, training)
+    logits = unet_decode(sd, feats, training)
     if return_features:
-        return logits, [x1, x2, x3, x4, x5]
+        return logits, feats
     return logits
+
+
+# ---------------------------------------------------------------------------------------------
+# late fusion (lf_model.py)
+# ---------------------------------------------------------------------------------------------
+LF_BATCH_KEYS = (('image', 'ms_image'), ('dem', 'dem'), ('slope', 'slope'), ('preflood', 'preflood'),
+                 ('pre_post_difference', 'pre_post_difference'), ('hand', 'hand'))   # lf_model.py:60-81
+LF_FEAT_SIZES = (64, 128, 256, 512, 512)                                             # lf_model.py:42
+
+
+def _init_double_conv(sd, prefix, cin, mid, cout):
+    for idx, (ci, co) in ((0, (cin, mid)), (3, (mid, cout))):
+        conv = nn.Conv2d(ci, co, kernel_size=3, padding=1)
+        bn = nn.BatchNorm2d(co)
+        sd[f"{prefix}.{idx}.weight"] = conv.weight.detach().clone()
+        sd[f"{prefix}.{idx}.bias"] = conv.bias.detach().clone()
+        for k, v in bn.state_dict().items():
+            sd[f"{prefix}.{idx + 1}.{k}"] = v.detach().clone()
+
+
+def init_lf_state_dict(in_channels: Dict[str, int], n_classes: int,
+                       seed: Optional[int] = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Fresh late-fusion parameters, consuming the RNG in the order of
+    ``LateFusionModel._build_model`` (lf_model.py:29-45): one UNetEncoder per input in dict
+    order, the UNetDecoder (up1..up4, outc), then the five concat convs."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    dcs = _double_convs(0)
+    for name, c in in_channels.items():
+        for prefix, cin, mid, cout in dcs[:5]:
+            _init_double_conv(sd, f"encoders.{name}.{prefix}", c if prefix.startswith("inc") else cin, mid, cout)
+    for prefix, cin, mid, cout in dcs[5:]:
+        _init_double_conv(sd, f"decoder.{prefix}", cin, mid, cout)
+    head = nn.Conv2d(64, n_classes, kernel_size=1)
+    sd["decoder.outc.conv.weight"] = head.weight.detach().clone()
+    sd["decoder.outc.conv.bias"] = head.bias.detach().clone()
+    for i, fs in enumerate(LF_FEAT_SIZES):
+        cc = nn.Conv2d(fs * len(in_channels), fs, 1, 1)
+        sd[f"concat_convs.{i}.weight"] = cc.weight.detach().clone()
+        sd[f"concat_convs.{i}.bias"] = cc.bias.detach().clone()
+    return sd
+
+
+def lf_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], training: bool = True):
+    """lf_model.py:58-92 -- per-modality encoders, per-level torch.concat in the fixed key
+    order, 1x1 concat_convs, decoder."""
+    feats = None
+    for bkey, enc in LF_BATCH_KEYS:
+        if bkey != 'image' and bkey not in batch:
+            continue
+        f = unet_encode(sd, batch[bkey], training, prefix=f"encoders.{enc}.")
+        feats = f if feats is None else [torch.concat([a, b], dim=1) for a, b in zip(feats, f)]
+    fused = []
+    for i, f in enumerate(feats):
+        if _EMULATE_BF16:
+            fused.append(_bf16(F.conv2d(f, _bf16(sd[f"concat_convs.{i}.weight"]), sd[f"concat_convs.{i}.bias"])))
+        else:
+            fused.append(F.conv2d(f, sd[f"concat_convs.{i}.weight"], sd[f"concat_convs.{i}.bias"]))
+    return unet_decode(sd, fused, training, prefix="decoder.")
+
+
+def lf_forward_bf16_emulated(sd, batch, training: bool = True):
+    """Late-fusion forward with the CUDA path's bf16 storage points emulated (diagnostic)."""
+    global _EMULATE_BF16
+    _EMULATE_BF16 = True
+    try:
+        b = {k: (_bf16(v) if v.is_floating_point() else v) for k, v in batch.items()}
+        return lf_forward(sd, b, training)
+    finally:
+        _EMULATE_BF16 = False
+
+
+def lf_training_step(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor],
+                     ignore_index: Optional[int], emulate_bf16: bool = False):
+    """One late-fusion training step (water_seg_model.py:98-136 with lf_model.forward)."""
+    keys = trainable_keys(sd)
+    for k in keys:
+        sd[k].requires_grad_(True)
+        sd[k].grad = None
+    logits = lf_forward_bf16_emulated(sd, batch, True) if emulate_bf16 else lf_forward(sd, batch, True)
+    loss, pred = masked_ce(logits, batch['target'], ignore_index)
+    loss.backward()
+    grads = {k: (sd[k].grad.detach().clone() if sd[k].grad is not None else torch.zeros_like(sd[k]))
+             for k in keys}
+    for k in keys:
+        sd[k].requires_grad_(False)
+        sd[k].grad = None
+    return loss.detach(), pred, logits.detach(), grads
 
 
 def early_fusion_input(batch: Dict[str, torch.Tensor]) -> torch.Tensor:

@@ -6,7 +6,8 @@ imports ``st_water_seg/models/unet.py`` and ``st_water_seg/datasets/utils.py`` b
 CPU fp32 with fixed seeds and stores small input/output vectors in ``tests/golden/*.pt``.
 The GPU box has no /root/reference; tests there read only the fixtures.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # everything
+    python tests/golden/make_golden.py lf       # only the late-fusion fixture
 """
 import importlib.util
 import sys
@@ -123,7 +124,87 @@ def tiler_case():
     print("tiler", {k: v["count"] for k, v in fx.items()})
 
 
+def _stub_reference_deps():
+    """The reference package imports pytorch_lightning / torchmetrics / omegaconf-based tools at
+    module import; none is installed here and none takes part in the arithmetic of forward /
+    loss / backward, so minimal stand-ins let the UNMODIFIED st_water_seg.models.lf_model (and
+    water_seg_model, unet) be imported and run."""
+    pl = types.ModuleType("pytorch_lightning")
+    pl.LightningModule = nn.Module
+    sys.modules.setdefault("pytorch_lightning", pl)
+
+    tm = types.ModuleType("torchmetrics")
+
+    class _Metric:
+        def __init__(self, *a, **k):
+            pass
+
+    class _Collection(_Metric):
+        def clone(self, prefix=None):
+            return self
+
+    tm.MetricCollection = _Collection
+    tm.F1Score = tm.JaccardIndex = tm.Accuracy = _Metric
+    sys.modules.setdefault("torchmetrics", tm)
+    tools = types.ModuleType("st_water_seg.tools")
+    tools.create_conf_matrix_pred_image = lambda *a, **k: None
+    sys.modules.setdefault("st_water_seg.tools", tools)
+    if str(REF.parent) not in sys.path:
+        sys.path.insert(0, str(REF.parent))
+
+
+def lf_case(name, in_channels, n, h, w, n_classes, ignore_index, seed, block=8):
+    """Late fusion: the reference's own LateFusionModel (lf_model.py) on CPU fp32."""
+    _stub_reference_deps()
+    from st_water_seg.models.lf_model import LateFusionModel
+    sys.path.insert(0, str(OUT.parent.parent))
+    from oracle import unet_oracle as O
+    torch.manual_seed(seed)
+    model = LateFusionModel(dict(in_channels), n_classes, 1e-4, ignore_index=ignore_index)
+    init_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = O.synthetic_batch(n, in_channels["ms_image"], h, w, seed=seed + 1, block=block)
+    g = torch.Generator().manual_seed(seed + 2)
+    for key, c in in_channels.items():
+        if key != "ms_image":
+            batch[key] = torch.rand(n, c, h, w, generator=g)
+    model._set_model_to_train()
+    logits = model.forward(batch)
+    loss = model.loss_func(logits, batch["target"])
+    if torch.isnan(loss):
+        loss = torch.nan_to_num(loss)
+    pred = logits.argmax(dim=1)
+    loss.backward()
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+    after = model.state_dict()
+    model._set_model_to_eval()
+    with torch.no_grad():
+        logits_eval = model.forward(batch)
+        enc_feats = model.encoders["ms_image"](batch["image"])
+    fx = {
+        "cfg": dict(in_channels=dict(in_channels), n=n, h=h, w=w, n_classes=n_classes,
+                    ignore_index=ignore_index, seed=seed),
+        "state_dict_keys": list(init_sd.keys()),
+        "init_checksum": {k: float(v.double().sum()) for k, v in init_sd.items()},
+        "batch": batch,
+        "logits_train": logits.detach().clone(), "loss": float(loss.detach()), "pred": pred.clone(),
+        "grads": summarize_grads(grads),
+        "grad_full": {k: grads[k].detach().clone() for k in
+                      ("concat_convs.0.weight", "concat_convs.0.bias", "concat_convs.4.bias",
+                       "decoder.outc.conv.weight", "encoders.dem.inc.double_conv.0.weight",
+                       "encoders.ms_image.inc.double_conv.1.weight")},
+        "bn_after": {k: after[k].clone() for k in after if k.startswith("encoders.dem.inc.double_conv.1.")},
+        "logits_eval": logits_eval.clone(),
+        "enc_feat_eval_checksum": [float(f.double().sum()) for f in enc_feats],
+        "enc_feat_eval_x5": enc_feats[4].clone(),
+    }
+    torch.save(fx, OUT / f"{name}.pt")
+    print(name, "loss", float(loss.detach()), "bytes", (OUT / f"{name}.pt").stat().st_size)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "lf":
+        lf_case("lf_c4_dem1_32", {"ms_image": 4, "dem": 1}, n=2, h=32, w=32, n_classes=3, ignore_index=0, seed=11)
+        sys.exit(0)
     ref_unet = load_by_path("ref_unet", REF / "models" / "unet.py")
     unet_case(ref_unet, "unet_c4_32", n=2, c=4, h=32, w=32, n_classes=3, ignore_index=0, seed=0)
     unet_case(ref_unet, "unet_c4_44x36", n=1, c=4, h=44, w=36, n_classes=3, ignore_index=0, seed=3)
@@ -132,3 +213,4 @@ if __name__ == "__main__":
               extra="all_ignored")
     op_semantics_case()
     tiler_case()
+    lf_case("lf_c4_dem1_32", {"ms_image": 4, "dem": 1}, n=2, h=32, w=32, n_classes=3, ignore_index=0, seed=11)

@@ -121,3 +121,47 @@ def test_metrics_micro():
     assert float(out["train_MulticlassAccuracy"]) == pytest.approx(ref["Accuracy"])
     assert float(out["train_MulticlassJaccardIndex"]) == pytest.approx(ref["Jaccard"])
     assert float(m.compute()["train_MulticlassF1Score"]) == pytest.approx(ref["F1"])
+
+
+def test_late_fusion_module_tree_equals_reference():
+    """state_dict keys / shapes / default init of LateFusionModel vs the fixture written by the
+    reference's own lf_model.LateFusionModel (tests/golden/make_golden.py lf)."""
+    from floodplanet_code_b200.lf_model import LateFusionModel
+    from floodplanet_code_b200.unet import UNetDecoder, UNetEncoder
+    from floodplanet_code_b200.water_seg_model import MODELS, build_model
+    fx = torch.load(GOLDEN / "lf_c4_dem1_32.pt", weights_only=False)
+    cfg = fx["cfg"]
+    assert MODELS["lf_model"] is LateFusionModel
+    want = ["self", "in_channels", "n_classes", "lr", "log_image_iter", "to_rgb_fcn", "ignore_index",
+            "optimizer_name", "feat_fusion"]
+    assert list(inspect.signature(LateFusionModel.__init__).parameters) == want
+    assert list(inspect.signature(UNetEncoder.__init__).parameters) == [
+        "self", "n_channels", "bilinear", "base_feat_channels"]
+    assert list(inspect.signature(UNetDecoder.__init__).parameters) == [
+        "self", "n_classes", "bilinear", "channel_factor", "base_feat_channels"]
+    torch.manual_seed(cfg["seed"])
+    m = build_model("lf_model", dict(cfg["in_channels"]), cfg["n_classes"], 1e-4, 50, None,
+                    cfg["ignore_index"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == fx["state_dict_keys"]
+    for k, v in fx["init_checksum"].items():
+        assert float(sd[k].double().sum()) == pytest.approx(v, rel=1e-12, abs=1e-12), k
+    assert sd["concat_convs.3.weight"].shape == (512, 1024, 1, 1)
+    # every trainable parameter is covered by the engine's gradient slab, once
+    names = m._engine.names
+    assert sorted(names) == sorted(k for k, _ in m.named_parameters())
+    assert len(set(names)) == len(names)
+    m.load_state_dict(O.init_lf_state_dict(cfg["in_channels"], cfg["n_classes"], seed=0), strict=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.forward({"image": torch.zeros(1, 4, 32, 32), "dem": torch.zeros(1, 1, 32, 32)})
+    with pytest.raises(KeyError):   # a raster without an encoder: KeyError as in the reference
+        m.forward({"image": torch.zeros(1, 4, 32, 32), "slope": torch.zeros(1, 1, 32, 32)})
+
+
+def test_encoder_decoder_halves_share_unet_names():
+    from floodplanet_code_b200.engine import DecoderEngine, EncoderEngine, UNetEngine
+    u = UNetEngine(4, 3)
+    assert EncoderEngine(4).names + DecoderEngine(3).names == u.names
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        from floodplanet_code_b200.unet import UNet
+        UNet(4, 3).encode(torch.zeros(1, 4, 32, 32))

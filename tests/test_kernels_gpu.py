@@ -512,3 +512,70 @@ def test_error_status_raises_runtime_error(ops):
         ops.conv3x3_fprop(x, torch.empty(64, 9, 24, dtype=torch.bfloat16, device="cuda"), y)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.ingest([torch.zeros(1, 4, 16, 16)], 16)
+
+
+# ---------------------------------------------------------------------------------------------
+# pointwise convolution + feature-level seams (late fusion, encode/decode API)
+# ---------------------------------------------------------------------------------------------
+PW_SHAPES = [
+    # n, h, w, cin, cout
+    (2, 16, 16, 64, 64),
+    (1, 32, 32, 128, 64),
+    (2, 20, 24, 256, 128),     # ragged patches
+    (1, 37, 37, 128, 64),      # odd size
+    (1, 8, 8, 1024, 512),
+    (3, 18, 18, 512, 256),
+    (1, 16, 16, 192, 64),      # three modalities at level 0
+]
+
+
+def rand_w1(cout, cin, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    w = torch.randn(cout, cin, 1, 1, generator=g, device="cuda") / math.sqrt(cin)
+    return w.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", PW_SHAPES)
+def test_conv1x1_fprop_dgrad_wgrad(ops, n, h, w, cin, cout):
+    x = rand_act(n, h, w, cin, 11)
+    wt = rand_w1(cout, cin, 12)
+    bias = torch.randn(cout, device="cuda")
+    # forward, written into a channel slice of a wider buffer (the decoder's concat buffer)
+    wide = torch.zeros(n, h, w, 2 * cout, dtype=torch.bfloat16, device="cuda")
+    y = wide[..., :cout]
+    ops.conv1x1(x, ops.repack_1x1(wt, False), y, torch.ones(cout, device="cuda"), bias)
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(x.float()), wt, bias)
+    assert rel(nchw(y.float()), ref) < 1e-2
+    assert float(wide[..., cout:].abs().max()) == 0.0          # neighbouring channels untouched
+    # data gradient
+    dy = rand_act(n, h, w, cout, 13)
+    dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device="cuda")
+    ops.conv1x1(dy, ops.repack_1x1(wt, True), dx)
+    ref_dx = F.conv_transpose2d(nchw(dy.float()), wt)
+    assert rel(nchw(dx.float()), ref_dx) < 2e-2
+    # weight gradient (x read from a channel slice too)
+    ws = torch.empty(ops.conv1x1_wgrad_workspace_bytes(n, h, w, cin, cout) // 4, device="cuda")
+    dw = torch.empty(cout, cin, 1, 1, device="cuda")
+    ops.conv1x1_wgrad(x, dy, dw, ws)
+    ref_dw = torch.einsum("nhwo,nhwi->oi", dy.float(), x.float())
+    assert rel(dw.view(cout, cin), ref_dw) < 2e-2
+    dw2 = torch.empty_like(dw)
+    ops.conv1x1_wgrad(x, dy, dw2, ws)
+    assert torch.equal(dw, dw2)                                 # deterministic
+    # bias gradient
+    db = torch.empty(cout, device="cuda")
+    ops.channel_sum(dy, db)
+    assert rel(db, dy.float().sum((0, 1, 2))) < 1e-3
+
+
+@pytest.mark.parametrize("n,c,h,w", [(2, 64, 16, 16), (1, 128, 37, 37), (2, 512, 5, 7), (1, 8, 9, 9)])
+def test_feature_layout_round_trip(ops, n, c, h, w):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.randn(n, c, h, w, generator=g, device="cuda")
+    wide = torch.zeros(n, h, w, c + 64, dtype=torch.bfloat16, device="cuda")
+    ops.nchw_f32_to_nhwc_bf16(src, wide[..., :c])
+    assert torch.equal(wide[..., :c], nhwc(src).to(torch.bfloat16))     # bit-exact cast + transpose
+    assert float(wide[..., c:].abs().max()) == 0.0
+    back = ops.nhwc_bf16_to_nchw_f32(wide[..., :c])
+    assert torch.equal(back, src.to(torch.bfloat16).float())

@@ -97,3 +97,39 @@ def test_micro_metrics_formulas():
     m = O.micro_metrics(conf)
     assert m["Accuracy"] == pytest.approx(0.5) and m["F1"] == pytest.approx(0.5)
     assert m["Jaccard"] == pytest.approx(5 / 15)
+
+
+def test_late_fusion_oracle_matches_reference_golden():
+    """Fixture made by the reference's own LateFusionModel (lf_model.py) on CPU fp32."""
+    fx = load("lf_c4_dem1_32")
+    cfg = fx["cfg"]
+    sd = O.init_lf_state_dict(cfg["in_channels"], cfg["n_classes"], seed=cfg["seed"])
+    assert list(sd.keys()) == fx["state_dict_keys"]          # state_dict key order of the reference
+    for k, v in fx["init_checksum"].items():
+        assert float(sd[k].double().sum()) == pytest.approx(v, rel=1e-12, abs=1e-12), k
+    loss, pred, logits, grads = O.lf_training_step(sd, fx["batch"], cfg["ignore_index"])
+    assert torch.allclose(logits, fx["logits_train"], rtol=1e-5, atol=1e-6)
+    assert float(loss) == pytest.approx(fx["loss"], rel=1e-5, abs=1e-7)
+    assert torch.equal(pred, fx["pred"])
+    for k, g in fx["grads"].items():
+        assert float(grads[k].double().norm()) == pytest.approx(g["norm"], rel=2e-4, abs=1e-9), k
+    for k, g in fx["grad_full"].items():
+        assert torch.allclose(grads[k], g, rtol=1e-3, atol=1e-7), k
+    for k, v in fx["bn_after"].items():
+        assert torch.allclose(sd[k].to(v.dtype), v, rtol=1e-5, atol=1e-7), k
+    with torch.no_grad():
+        ev = O.lf_forward(sd, fx["batch"], training=False)
+        feats = O.unet_encode(sd, fx["batch"]["image"], training=False, prefix="encoders.ms_image.")
+    assert torch.allclose(ev, fx["logits_eval"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(feats[4], fx["enc_feat_eval_x5"], rtol=1e-4, atol=1e-5)
+    for f, want in zip(feats, fx["enc_feat_eval_checksum"]):
+        assert float(f.double().sum()) == pytest.approx(want, rel=1e-4)
+
+
+def test_encode_decode_compose_to_forward():
+    sd = O.init_state_dict(4, 3, seed=2)
+    x = torch.rand(1, 4, 32, 32, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        a = O.unet_forward(sd, x, training=False)
+        b = O.unet_decode(sd, O.unet_encode(sd, x, training=False), training=False)
+    assert torch.equal(a, b)

@@ -375,15 +375,25 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float sc0 = s_scale[cb], sc1 = s_scale[cb + 1], sh0 = s_shift[cb], sh1 = s_shift[cb + 1];
             const float mu0 = s_mean[cb], mu1 = s_mean[cb + 1], is0 = s_invstd[cb], is1 = s_invstd[cb + 1];
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              if ((vmask >> rr) & 1u) {
+            // rows are read in batches of 8 independent loads (a branch per row serialises the
+            // shared-memory latency: measured ~35 cycles per row on the epilogue's critical path);
+            // rows outside the image contribute through a 0/1 factor instead of a branch
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              uint32_t gv[8], yv[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int rr = r0 + j;
                 const uint32_t off = rr * 128 + (uint32_t((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4;
-                const uint32_t gv = ld_shared_u32(stg + off);
-                const uint32_t yv = ld_shared_u32(ybuf + off);
-                const float y0 = bf16_lo(yv), y1 = bf16_hi(yv);
-                const float g0 = fmaf(y0, sc0, sh0) > 0.f ? bf16_lo(gv) : 0.f;
-                const float g1 = fmaf(y1, sc1, sh1) > 0.f ? bf16_hi(gv) : 0.f;
+                gv[j] = ld_shared_u32(stg + off);
+                yv[j] = ld_shared_u32(ybuf + off);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const bool ok = (vmask >> (r0 + j)) & 1u;
+                const float y0 = bf16_lo(yv[j]), y1 = bf16_hi(yv[j]);
+                const float g0 = (ok && fmaf(y0, sc0, sh0) > 0.f) ? bf16_lo(gv[j]) : 0.f;
+                const float g1 = (ok && fmaf(y1, sc1, sh1) > 0.f) ? bf16_hi(gv[j]) : 0.f;
                 s0 += g0; s1 += g1;
                 q0 = fmaf(g0, (y0 - mu0) * is0, q0);
                 q1 = fmaf(g1, (y1 - mu1) * is1, q1);
@@ -394,12 +404,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else if (do_stats) {
             // lane l owns channels 2l, 2l+1 of this unit: walk the 32 staged rows
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              if ((vmask >> rr) & 1u) {
-                const uint32_t wv = ld_shared_u32(stg + rr * 128 +
-                                                  (uint32_t((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
-                const float lo = bf16_lo(wv), hi = bf16_hi(wv);
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              uint32_t wv[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int rr = r0 + j;
+                wv[j] = ld_shared_u32(stg + rr * 128 + (uint32_t((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const bool ok = (vmask >> (r0 + j)) & 1u;
+                const float lo = ok ? bf16_lo(wv[j]) : 0.f, hi = ok ? bf16_hi(wv[j]) : 0.f;
                 s0 += lo; s1 += hi;
                 q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
               }

@@ -579,3 +579,79 @@ def test_feature_layout_round_trip(ops, n, c, h, w):
     assert float(wide[..., c:].abs().max()) == 0.0
     back = ops.nhwc_bf16_to_nchw_f32(wide[..., :c])
     assert torch.equal(back, src.to(torch.bfloat16).float())
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes (per-GPU batch 64, 512x512): size-independent properties
+# ---------------------------------------------------------------------------------------------
+def _dot(a, b):
+    return float((a.double() * b.double()).sum())
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, 512), (128, 64, 512), (256, 128, 256)])
+def test_full_size_conv_adjoint_identities(ops, cin, cout, hw):
+    """At the bench shapes the torch reference conv would take minutes on the host, so the three
+    conv kernels are checked against EACH OTHER through the identities that make them one
+    operator and its adjoints (every term evaluated by a different kernel):
+        <conv(x, W), dy> = <x, dgrad(dy, W)> = <W, wgrad(x, dy)>
+    plus linearity of fprop and the fused BatchNorm sums against a plain reduction."""
+    n = 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.rand(n, hw, hw, cin, generator=g, device="cuda") - 0.3).to(torch.bfloat16)
+    wt = rand_w(cout, cin, 3)
+    y = torch.empty(n, hw, hw, cout, dtype=torch.bfloat16, device="cuda")
+    parts = torch.empty(ops.stat_rows(), 2, cout, dtype=torch.float32, device="cuda")
+    ops.conv3x3_fprop(x, ops.repack_fprop(wt, cin), y, stat_partials=parts)
+    # dy correlated with y, so the inner products are O(|y|^2) and not a sum of random signs
+    dy = torch.randn(n, hw, hw, cout, generator=g, device="cuda").mul_(0.5).add_(y.float()).to(torch.bfloat16)
+    dx = torch.empty_like(x)
+    ops.conv3x3_dgrad(dy, ops.repack_dgrad(wt), dx)
+    dw = torch.empty(cout, cin, 3, 3, device="cuda")
+    ws = torch.empty(ops.wgrad_workspace_bytes(n, hw, hw, cin, cout) // 4, device="cuda")
+    ops.conv3x3_wgrad(x, dy, dw, ws, cin)
+    torch.cuda.synchronize()
+    a = _dot(y, dy)          # <conv(x,W), dy>      (y rounded to bf16: ~2^-9 relative, random sign)
+    b = _dot(x, dx)          # <x, dgrad(dy,W)>
+    c = _dot(wt, dw)         # <W, wgrad(x,dy)>     (fp32 output)
+    assert c > 0.3 * float(y.double().norm()) ** 2
+    assert abs(a - c) < 1e-3 * c and abs(b - c) < 1e-3 * c, (a, b, c)
+    # fused BatchNorm statistics = plain reductions of the stored tensor
+    s = parts.double().sum(0)
+    yd = y.double()
+    assert float((s[0] - yd.sum((0, 1, 2))).abs().max()) < 1e-6 * float(yd.abs().sum((0, 1, 2)).max())
+    assert torch.allclose(s[1], (yd * yd).sum((0, 1, 2)), rtol=1e-4)
+    # linearity: conv(2x) = 2 conv(x) exactly (power-of-two scaling commutes with every rounding)
+    y2 = torch.empty_like(y)
+    ops.conv3x3_fprop((x.float() * 2).to(torch.bfloat16), ops.repack_fprop(wt, cin), y2)
+    assert torch.equal(y2.float(), y.float() * 2)
+    # determinism run to run (split-K wgrad included)
+    dw2 = torch.empty_like(dw)
+    ops.conv3x3_wgrad(x, dy, dw2, ws, cin)
+    assert torch.equal(dw, dw2)
+
+
+def test_full_size_pool_and_elementwise_properties(ops):
+    """Batch 64 x 512 x 512 x 64: max-pool of the fused kernel equals pooling its own activation
+    output, indices reproduce the pooled values (gather), pool-backward scatters exactly the
+    incoming gradient mass."""
+    n, hw, c = 64, 512, 64
+    g = torch.Generator(device="cuda").manual_seed(9)
+    y = torch.randn(n, hw, hw, c, generator=g, device="cuda").to(torch.bfloat16)
+    scale = torch.rand(c, generator=g, device="cuda") + 0.5
+    shift = torch.randn(c, generator=g, device="cuda") * 0.1
+    a = torch.empty_like(y)
+    pooled = torch.empty(n, hw // 2, hw // 2, c, dtype=torch.bfloat16, device="cuda")
+    idx = torch.empty(n, hw // 2, hw // 2, c, dtype=torch.uint8, device="cuda")
+    ops.bn_apply_relu_maxpool2(y, a, pooled, idx, scale, shift)
+    win = a.view(n, hw // 2, 2, hw // 2, 2, c).permute(0, 1, 3, 5, 2, 4).reshape(n, hw // 2, hw // 2, c, 4)
+    assert torch.equal(pooled, win.max(-1).values)                                   # bit-exact
+    assert torch.equal(pooled, win.gather(-1, idx.long().unsqueeze(-1)).squeeze(-1))  # indices point at the max
+    assert int(idx.max()) <= 3
+    first = (win == pooled.unsqueeze(-1)).float().argmax(-1)                          # first maximum wins
+    assert torch.equal(first, idx.long())
+    del win, first
+    dp = torch.randn(n, hw // 2, hw // 2, c, generator=g, device="cuda").to(torch.bfloat16)
+    dxp = torch.empty_like(y)
+    ops.maxpool2_bwd(dp, idx, None, dxp)
+    assert int((dxp != 0).sum()) <= dp.numel()
+    assert torch.equal(dxp.view(n, hw // 2, 2, hw // 2, 2, c).float().sum((2, 4)).to(torch.bfloat16), dp)

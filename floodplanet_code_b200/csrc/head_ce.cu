@@ -9,6 +9,13 @@ namespace fp {
 constexpr int kMaxClasses = 8;
 constexpr int kHeadC = 64;
 
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
   f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
@@ -17,66 +24,114 @@ __device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------
-// head forward: one thread per pixel, 8 x 16-byte loads, weights broadcast from smem
+// head forward: 8 lanes x 8 channels cover one pixel and a warp iteration covers 32 pixels
+// (8 independent, fully coalesced 16-byte loads per lane in flight).  The 8 x NC partial dot
+// products of a lane are summed across its 8-lane group with a TRANSPOSING butterfly (each
+// step halves the number of live values), which leaves lane (sub, cg) with the finished
+// logits of pixel base + 4*cg + sub: the 32 lanes then store 32 consecutive floats per class.
+// (The first version used one thread per pixel: 16-byte loads 128 bytes apart and 3*64
+// shared-memory weight reads per pixel held it at 3.2 TB/s.)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kHeadFwdThreads = 256;
+
+template <int NC>
+__global__ void __launch_bounds__(kHeadFwdThreads)
 head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const float* __restrict__ w,
                    const float* __restrict__ b, float* __restrict__ logits, int N, long hw,
                    int ncls, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift) {
-  __shared__ float sw[kMaxClasses * kHeadC];
-  __shared__ float sb[kMaxClasses];
-  __shared__ float s_sc[kHeadC], s_sh[kHeadC];
-  for (int i = threadIdx.x; i < ncls * kHeadC; i += blockDim.x) sw[i] = w[i];
-  if (threadIdx.x < ncls) sb[threadIdx.x] = b[threadIdx.x];
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 3;  // which pixel of a quad
+  const int cg = lane & 7;    // channel group: channels cg*8 .. cg*8+7
   const bool fused_bn = bn_scale != nullptr;   // x is the raw conv output: a = relu(x*scale+shift)
-  if (fused_bn && threadIdx.x < kHeadC) {
-    s_sc[threadIdx.x] = bn_scale[threadIdx.x];
-    s_sh[threadIdx.x] = bn_shift[threadIdx.x];
+  float wr[NC][8], sc[8], sh[8], bias[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    bias[k] = k < ncls ? __ldg(b + k) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[k][j] = k < ncls ? __ldg(w + k * kHeadC + cg * 8 + j) : 0.f;
   }
-  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = fused_bn ? __ldg(bn_scale + cg * 8 + j) : 1.f;
+    sh[j] = fused_bn ? __ldg(bn_shift + cg * 8 + j) : 0.f;
+  }
   const long total = (long)N * hw;
-  for (long px = blockIdx.x * (long)blockDim.x + threadIdx.x; px < total;
-       px += (long)gridDim.x * blockDim.x) {
-    float acc[kMaxClasses];
+  const long warps_total = (long)gridDim.x * (kHeadFwdThreads / 32);
+  for (long base = ((long)blockIdx.x * (kHeadFwdThreads / 32) + (threadIdx.x >> 5)) * 32; base < total;
+       base += warps_total * 32) {
+    uint4 q[8];
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
-    const uint4* row = reinterpret_cast<const uint4*>(x + px * ldx);
+    for (int u = 0; u < 8; ++u) {
+      const long px = base + u * 4 + sub;
+      q[u] = px < total ? ld_nc_v4(x + px * ldx + cg * 8) : make_uint4(0, 0, 0, 0);
+    }
+    float acc[8][NC];
 #pragma unroll
-    for (int g = 0; g < kHeadC / 8; ++g) {
+    for (int u = 0; u < 8; ++u) {
       float f[8];
-      unpack8h(__ldg(row + g), f);
+      unpack8h(q[u], f);
       if (fused_bn) {
         // same arithmetic and bf16 rounding as bn_apply_relu, so fusing changes no bit
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-          const uint32_t pk = pack_bf16x2(fmaxf(fmaf(f[j], s_sc[g * 8 + j], s_sh[g * 8 + j]), 0.f),
-                                          fmaxf(fmaf(f[j + 1], s_sc[g * 8 + j + 1], s_sh[g * 8 + j + 1]), 0.f));
+          const uint32_t pk = pack_bf16x2(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f),
+                                          fmaxf(fmaf(f[j + 1], sc[j + 1], sh[j + 1]), 0.f));
           f[j] = bf16_lo(pk);
           f[j + 1] = bf16_hi(pk);
         }
       }
 #pragma unroll
-      for (int k = 0; k < kMaxClasses; ++k) {
-        if (k < ncls) {
+      for (int k = 0; k < NC; ++k) {
+        float a = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], sw[k * kHeadC + g * 8 + j], acc[k]);
-        }
+        for (int j = 0; j < 8; ++j) a = fmaf(f[j], wr[k][j], a);
+        acc[u][k] = a;
       }
     }
-    const long n = px / hw, o = px - n * hw;
+    // transposing butterfly over the 8 lanes of a pixel: after the step with lane mask m a lane
+    // keeps the pixels u whose bit m equals its own bit m
+    float r4[4][NC], r2[2][NC], r1[NC];
+    const bool b4 = cg & 4, b2 = cg & 2, b1 = cg & 1;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
-      if (k < ncls) logits[((long)n * ncls + k) * hw + o] = acc[k] + sb[k];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const float mine = b4 ? acc[i + 4][k] : acc[i][k];
+        const float theirs = b4 ? acc[i][k] : acc[i + 4][k];
+        r4[i][k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const float mine = b2 ? r4[i + 2][k] : r4[i][k];
+        const float theirs = b2 ? r4[i][k] : r4[i + 2][k];
+        r2[i][k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 2);
+      }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const float mine = b1 ? r2[1][k] : r2[0][k];
+      const float theirs = b1 ? r2[0][k] : r2[1][k];
+      r1[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 1);
+    }
+    const long px = base + cg * 4 + sub;   // u == cg
+    if (px < total) {
+      const long n = px / hw, o = px - n * hw;
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+        if (k < ncls) logits[((long)n * ncls + k) * hw + o] = r1[k] + bias[k];
+    }
   }
 }
 
 // ---------------------------------------------------------------------------
-// head backward: 8 lanes x 8 channels cover one pixel, 8 pixels (two quads) per warp
-// iteration so that two independent 16-byte loads per lane are in flight.
+// head backward: 8 lanes x 8 channels cover one pixel, kHeadBwdPx pixels per warp iteration
+// with all of a lane's 16-byte loads issued before the first use.
 //   dx[p, c]  = sum_k dl[k, p] * w[k, c]
 //   dW[k, c] += dl[k, p] * x[p, c],   db[k] += dl[k, p]
 // ---------------------------------------------------------------------------
 constexpr int kHeadBwdThreads = 256;
+constexpr int kHeadBwdPx = 16;   // pixels per warp iteration (4 per quad lane; 8 spills at 128 registers)
 
 template <int NC, bool FUSED>
 __global__ void __launch_bounds__(kHeadBwdThreads, 2)
@@ -117,70 +172,76 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
   }
   const long total = (long)N * hw;
   const long warps_total = (long)gridDim.x * (kHeadBwdThreads / 32);
-  for (long base = ((long)blockIdx.x * (kHeadBwdThreads / 32) + warp) * 8; base < total;
-       base += warps_total * 8) {
-    long px[2];
-    bool ok[2];
-    uint4 xin[2];
-    float dl[2][NC];
+  for (long base = ((long)blockIdx.x * (kHeadBwdThreads / 32) + warp) * kHeadBwdPx; base < total;
+       base += warps_total * kHeadBwdPx) {
+    constexpr int U = kHeadBwdPx / 4;
+    // all loads of the iteration first: U independent 16-byte loads of x per lane, and the
+    // iteration's dlogits as NC coalesced loads (lane L holds pixel base + L) that are then
+    // handed to the 8 lanes of each pixel by shuffles
+    uint4 xin[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      px[u] = base + u * 4 + sub;
-      ok[u] = px[u] < total;
-      if (ok[u]) {
-        xin[u] = __ldg(reinterpret_cast<const uint4*>(x + px[u] * ldx + cg * 8));
-        const long n = px[u] / hw, o = px[u] - n * hw;
+    for (int u = 0; u < U; ++u) {
+      const long px = base + u * 4 + sub;
+      xin[u] = px < total ? ld_nc_v4(x + px * ldx + cg * 8) : make_uint4(0, 0, 0, 0);
+    }
+    float dlv[NC];
+    {
+      const long px = base + lane;
+      const bool in = lane < kHeadBwdPx && px < total;
+      const long n = in ? px / hw : 0, o = in ? px - n * hw : 0;
 #pragma unroll
-        for (int k = 0; k < NC; ++k)
-          dl[u][k] = k < ncls ? __ldg(dlogits + ((long)n * ncls + k) * hw + o) : 0.f;
-      }
+      for (int k = 0; k < NC; ++k)
+        dlv[k] = (in && k < ncls) ? __ldg(dlogits + ((long)n * ncls + k) * hw + o) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (ok[u]) {
-        float f[8], g[8], yraw[8];
-        unpack8h(xin[u], f);
-        if (fused_bn) {
+    for (int u = 0; u < U; ++u) {
+      const long px = base + u * 4 + sub;
+      float dl[NC];
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            yraw[j] = f[j];
-            yraw[j + 1] = f[j + 1];
-            const uint32_t pk = pack_bf16x2(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f),
-                                            fmaxf(fmaf(f[j + 1], sc[j + 1], sh[j + 1]), 0.f));
-            f[j] = bf16_lo(pk);
-            f[j + 1] = bf16_hi(pk);
-          }
+      for (int k = 0; k < NC; ++k) dl[k] = __shfl_sync(0xffffffffu, dlv[k], u * 4 + sub);
+      float f[8], g[8], yraw[8];
+      unpack8h(xin[u], f);
+      if (fused_bn) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          yraw[j] = f[j];
+          yraw[j + 1] = f[j + 1];
+          const uint32_t pk = pack_bf16x2(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f),
+                                          fmaxf(fmaf(f[j + 1], sc[j + 1], sh[j + 1]), 0.f));
+          f[j] = bf16_lo(pk);
+          f[j + 1] = bf16_hi(pk);
         }
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          const float4 w0 = *reinterpret_cast<const float4*>(sw + k * kHeadC + cg * 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(sw + k * kHeadC + cg * 8 + 4);
-          const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      for (int k = 0; k < NC; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + k * kHeadC + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + k * kHeadC + cg * 8 + 4);
+        const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            g[j] = fmaf(dl[u][k], wk[j], g[j]);
-            dw[k][j] = fmaf(dl[u][k], f[j], dw[k][j]);
-          }
-          db[k] += dl[u][k];
+        for (int j = 0; j < 8; ++j) {
+          g[j] = fmaf(dl[k], wk[j], g[j]);
+          dw[k][j] = fmaf(dl[k], f[j], dw[k][j]);
         }
-        uint4 o4;
-        o4.x = pack_bf16x2(g[0], g[1]);
-        o4.y = pack_bf16x2(g[2], g[3]);
-        o4.z = pack_bf16x2(g[4], g[5]);
-        o4.w = pack_bf16x2(g[6], g[7]);
-        *reinterpret_cast<uint4*>(dx + px[u] * lddx + cg * 8) = o4;
-        if (fused_bn) {
-          // the sums use the bf16-rounded dx that is stored (what the apply pass will read)
-          float gr[8];
-          unpack8h(o4, gr);
+        db[k] += dl[k];
+      }
+      uint4 o4;
+      o4.x = pack_bf16x2(g[0], g[1]);
+      o4.y = pack_bf16x2(g[2], g[3]);
+      o4.z = pack_bf16x2(g[4], g[5]);
+      o4.w = pack_bf16x2(g[6], g[7]);
+      if (px < total) *reinterpret_cast<uint4*>(dx + px * lddx + cg * 8) = o4;
+      if (fused_bn) {
+        // the sums use the bf16-rounded dx that is stored (what the apply pass will read);
+        // out-of-range pixels have dl = 0, hence contribute exactly 0
+        float gr[8];
+        unpack8h(o4, gr);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float gg = fmaf(yraw[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
-            s1[j] += gg;
-            s2[j] = fmaf(gg, yraw[j], s2[j]);
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float gg = fmaf(yraw[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
+          s1[j] += gg;
+          s2[j] = fmaf(gg, yraw[j], s2[j]);
         }
       }
     }
@@ -463,10 +524,16 @@ int fpb200_head1x1_fwd(const void* x, long ldx, const float* w, const float* b, 
   if (C != kHeadC || n_classes < 1 || n_classes > kMaxClasses || ldx % 8 != 0)
     return FPB200_ERR_SHAPE;
   const long total = (long)N * H * W;
-  long g = (total + 255) / 256;
-  if (g > 148L * 16) g = 148L * 16;
-  head1x1_fwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, w, b, logits, N, (long)H * W, n_classes, bn_scale, bn_shift);
+  long g = (total + kHeadFwdThreads - 1) / kHeadFwdThreads;   // 32 pixels per warp iteration
+  if (g > 8L * sm_count()) g = 8L * sm_count();
+#define FP_HEAD_FWD(nc)                                                                         \
+  head1x1_fwd_kernel<nc><<<(int)g, kHeadFwdThreads, 0, (cudaStream_t)stream>>>(                 \
+      (const __nv_bfloat16*)x, ldx, w, b, logits, N, (long)H * W, n_classes, bn_scale, bn_shift)
+  if (n_classes <= 2) FP_HEAD_FWD(2);
+  else if (n_classes == 3) FP_HEAD_FWD(3);
+  else if (n_classes == 4) FP_HEAD_FWD(4);
+  else FP_HEAD_FWD(8);
+#undef FP_HEAD_FWD
   return check_launch("head1x1_fwd");
 }
 
@@ -485,7 +552,9 @@ int fpb200_head1x1_bwd(const float* dlogits, const void* x, long ldx, const floa
   head1x1_bwd_kernel<nc, fused><<<rows, kHeadBwdThreads, 0, (cudaStream_t)stream>>>(             \
       dlogits, (const __nv_bfloat16*)x, ldx, w, (__nv_bfloat16*)dx, lddx, partials, N, (long)H * W, \
       n_classes, bn_scale, bn_shift, bn_mean, bn_invstd, bn_partials)
-  if (n_classes <= 4) {
+  if (n_classes <= 3) {   // the reference's n_classes = 3: no padded class in registers
+    if (bn_scale != nullptr) FP_HEAD_BWD(3, true); else FP_HEAD_BWD(3, false);
+  } else if (n_classes == 4) {
     if (bn_scale != nullptr) FP_HEAD_BWD(4, true); else FP_HEAD_BWD(4, false);
   } else {
     if (bn_scale != nullptr) FP_HEAD_BWD(8, true); else FP_HEAD_BWD(8, false);

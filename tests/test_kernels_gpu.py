@@ -363,9 +363,11 @@ def test_bilinear_align_corners_golden(ops):
     assert float(out[0, 0, 0, 0]) == 0.0 and float(out[0, 0, 7, 0]) == 3.0
 
 
-@pytest.mark.parametrize("ncls", [2, 3])
-def test_head_fwd_bwd(ops, ncls):
-    n, h, w, c = 2, 20, 24, 64
+@pytest.mark.parametrize("ncls,hw", [(2, (20, 24)), (3, (20, 24)), (3, (19, 23)), (4, (7, 5)), (5, (9, 11))])
+def test_head_fwd_bwd(ops, ncls, hw):
+    # (19, 23), (7, 5), (9, 11): pixel counts that are not multiples of the 32 / 16 pixels a warp
+    # iteration covers, images that end inside a warp's pixel group
+    n, (h, w), c = 2, hw, 64
     x = rand_act(n, h, w, c, 23)
     g = torch.Generator(device="cuda").manual_seed(24)
     wt = torch.randn(ncls, c, generator=g, device="cuda") / 8

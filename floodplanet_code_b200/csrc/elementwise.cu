@@ -546,13 +546,37 @@ __device__ __forceinline__ void bilinear_src(int dst, float ratio, int in_size, 
 // One block per group of kUpRows output rows of one image.  The group's output rows read at most
 // kUpSrcRows consecutive source rows (ratio < 1/2), so each thread interpolates those source rows
 // HORIZONTALLY once (2 loads per source row instead of 4 per output row) and then mixes them
-// vertically with block-uniform taps; consecutive threads write
-// consecutive 16-byte channel groups.  (The first version loaded and unpacked 4 source vectors
-// per output vector and was instruction-issue bound at 3.2 TB/s, ncu: issue-active 78 %.)
+// vertically with block-uniform taps; consecutive threads write consecutive 16-byte channel
+// groups, a thread keeps its channel group for the whole block (no per-iteration division).
+// Interior groups of the x2 / align_corners pattern (output rows 2j-1 .. 2j+2 read source rows
+// (j-1,j) (j,j+1) (j,j+1) (j+1,j+2)) take a fully static path; the taps are still the ones
+// bilinear_src computes, the pattern is only CHECKED, so edge groups, padding rows and any
+// rounding surprise fall back to the generic walk.  History (ncu, 64ch 256->512, batch 64):
+// 4 loads per output vector 0.83 ms, issue-active 78 %; separable 0.69 ms, latency bound;
+// loads hoisted 0.61 ms, 121 instructions per stored vector, half of them tap bookkeeping.
 constexpr int kUpRows = 4;
 constexpr int kUpSrcRows = 4;
+constexpr int kUpThreads = 256;
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void hlerp8(const uint4& a, const uint4& b, float lw0, float lw1,
+                                       float (&o)[8]) {
+  float v0[8], v1[8];
+  unpack8(a, v0);
+  unpack8(b, v1);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = lw0 * v0[j] + lw1 * v1[j];
+}
+
+// lh0 * top + lh1 * bottom: same expression order as ATen's upsample_bilinear2d
+__device__ __forceinline__ uint4 vlerp8(const float (&top)[8], const float (&bot)[8], float lh0,
+                                        float lh1) {
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(lh1, bot[j], lh0 * top[j]);
+  return pack8(o);
+}
+
+__global__ void __launch_bounds__(kUpThreads)
 upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
                           __nv_bfloat16* __restrict__ out, long ldo, int h, int w, int Ho, int Wo,
                           int CG, int pad_top, int pad_left, float rh, float rw) {
@@ -580,14 +604,17 @@ upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
       src_used |= (1u << k0[r]) | (1u << k1[r]);
     }
   }
-  const int work = Wo * CG;
-  for (int i = threadIdx.x; i < work; i += blockDim.x) {
-    const int wo = i / CG;
-    const int cg = i - wo * CG;
+  const bool interior = row_in == 0xFu && k0[0] == 0 && k1[0] == 1 && k0[1] == 1 && k1[1] == 2 &&
+                        k0[2] == 1 && k1[2] == 2 && k0[3] == 2 && k1[3] == 3;
+  const int cols_per_pass = kUpThreads / CG;
+  const int cg = threadIdx.x % CG;
+  const int col0 = threadIdx.x / CG;
+  if (col0 >= cols_per_pass) return;
+  const long ostride = (long)Wo * ldo;
+  for (int wo = col0; wo < Wo; wo += cols_per_pass) {
     const int uw = wo - pad_left;
     const bool col_in = uw >= 0 && uw < 2 * w;
     __nv_bfloat16* orow = out + (((long)n * Ho + ho0) * Wo + wo) * ldo + cg * 8;
-    const long ostride = (long)Wo * ldo;
     if (!col_in || row_in == 0) {
 #pragma unroll
       for (int r = 0; r < kUpRows; ++r)
@@ -597,12 +624,8 @@ upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
     int w0, w1;
     float lw0, lw1;
     bilinear_src(uw, rw, w, w0, w1, lw0, lw1);
-    // walk the source rows once, keeping the previous horizontally-interpolated row: an output
-    // row is emitted when its lower tap has been computed (taps chosen by block-uniform
-    // compares, so everything stays in statically indexed registers)
     // all source vectors of the group are requested before the first use (8 independent 16-byte
-    // loads in flight per thread; rows beyond the image are clamped onto the last row = an L1 hit):
-    // the serial load -> use -> store chain per source row left the kernel latency bound
+    // loads in flight per thread; rows beyond the image are clamped onto the last row = an L1 hit)
     uint4 q0[kUpSrcRows], q1[kUpSrcRows];
 #pragma unroll
     for (int k = 0; k < kUpSrcRows; ++k) {
@@ -611,6 +634,21 @@ upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
       q0[k] = *reinterpret_cast<const uint4*>(rp + (long)w0 * ldx);
       q1[k] = *reinterpret_cast<const uint4*>(rp + (long)w1 * ldx);
     }
+    if (interior) {
+      float ha[8], hb[8];
+      hlerp8(q0[0], q1[0], lw0, lw1, ha);
+      hlerp8(q0[1], q1[1], lw0, lw1, hb);
+      *reinterpret_cast<uint4*>(orow) = vlerp8(ha, hb, lh0[0], lh1[0]);
+      hlerp8(q0[2], q1[2], lw0, lw1, ha);
+      *reinterpret_cast<uint4*>(orow + ostride) = vlerp8(hb, ha, lh0[1], lh1[1]);
+      *reinterpret_cast<uint4*>(orow + 2 * ostride) = vlerp8(hb, ha, lh0[2], lh1[2]);
+      hlerp8(q0[3], q1[3], lw0, lw1, hb);
+      *reinterpret_cast<uint4*>(orow + 3 * ostride) = vlerp8(ha, hb, lh0[3], lh1[3]);
+      continue;
+    }
+    // generic walk over the source rows, keeping the previous horizontally-interpolated row: an
+    // output row is emitted when its lower tap has been computed (taps chosen by block-uniform
+    // compares, so everything stays in statically indexed registers)
     float prev[8], cur[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) prev[j] = cur[j] = 0.f;
@@ -619,24 +657,12 @@ upsample2x_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
       if (!(src_used & (1u << k))) continue;       // block-uniform
 #pragma unroll
       for (int j = 0; j < 8; ++j) prev[j] = cur[j];
-      float v0[8], v1[8];
-      unpack8(q0[k], v0);
-      unpack8(q1[k], v1);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cur[j] = lw0 * v0[j] + lw1 * v1[j];
+      hlerp8(q0[k], q1[k], lw0, lw1, cur);
 #pragma unroll
       for (int r = 0; r < kUpRows; ++r) {
         if (!(row_in & (1u << r)) || k1[r] != k) continue;
-        // lh0 * top + lh1 * bottom: same expression order as ATen's upsample_bilinear2d
-        float o[8];
-        if (k0[r] == k) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = fmaf(lh1[r], cur[j], lh0[r] * cur[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = fmaf(lh1[r], cur[j], lh0[r] * prev[j]);
-        }
-        *reinterpret_cast<uint4*>(orow + r * ostride) = pack8(o);
+        if (k0[r] == k) *reinterpret_cast<uint4*>(orow + r * ostride) = vlerp8(cur, cur, lh0[r], lh1[r]);
+        else *reinterpret_cast<uint4*>(orow + r * ostride) = vlerp8(prev, cur, lh0[r], lh1[r]);
       }
     }
     // rows of the group that fall into the zero padding
@@ -666,108 +692,163 @@ __device__ __forceinline__ void bilinear_candidates(int i, float ratio, int in_s
 }
 
 constexpr int kUpMaxTaps = 8;
-constexpr int kUpBwdHalo = 12;  // extra output columns staged per chunk (conservative stencil reach)
+constexpr int kUpBwdHalo = 12;      // extra output columns staged per chunk (conservative stencil reach)
+constexpr int kUpBwdMaxCols = 64;   // source columns per block (size of the column tap table)
 
 __host__ __device__ inline int up_bwd_chunk_cols(int C) {   // source columns per block
   const int c = 4096 / C;
-  return c < 8 ? 8 : c;
+  return c < 8 ? 8 : (c > kUpBwdMaxCols ? kUpBwdMaxCols : c);
 }
 
-// Gather-form backward (deterministic, no atomics), separable in two stages per block
-// = (image, source row, chunk of source columns):
+constexpr int kUpBwdRows = 8;       // source rows per block (they share the column tap table)
+
+// Gather-form backward (deterministic, no atomics), separable in two stages.  One block =
+// (image, group of kUpBwdRows source rows, chunk of source columns); per source row:
 //   1. vertical:   V[ow][c] = sum over the <= 4 contributing output rows of wh * dout[oh][ow][c]
 //      for every output column the chunk can touch, fp32, into shared memory;
 //   2. horizontal: dx[wi][c] = sum over the <= 4 contributing output columns of ww * V[ow][c].
-// Global loads drop from ~16 to ~4 per staged output vector and the per-tap index arithmetic
-// from 16 to 4 + 4 evaluations (the one-stage version spent ~980 instructions per source vector
-// and ran at 2.2 TB/s, ncu: issue-active 76 %).
-__global__ void __launch_bounds__(256)
+// The taps (which output rows / columns touch a source row / column, with which weight) are
+// found with the forward's own bilinear_src arithmetic, once per block, one candidate per lane,
+// into shared-memory tables (one per source row of the group, one per source column of the chunk).
+// History (ncu, 64ch 512->256, batch 64): one stage, ~980 instructions per source vector, 2.2 TB/s;
+// two stages with per-thread tap search 1.12 ms; tables per (row, chunk) block 0.85 ms, still
+// issue bound (772 M warp instructions: 17 % tap search, 16 % 64-bit address multiplies); this
+// version amortises the tables over 8 rows and addresses with 32-bit offsets inside one image.
+__global__ void __launch_bounds__(kUpThreads)
 upsample2x_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long lddo,
                           __nv_bfloat16* __restrict__ dx, long lddx, int h, int w, int Ho, int Wo,
                           int CG, int pad_top, int pad_left, float rh, float rw, int chunk_cols,
-                          int chunks) {
-  extern __shared__ float s_v[];   // [2 * chunk_cols + kUpBwdHalo][CG * 8]
-  __shared__ int s_rows[kUpMaxTaps];
-  __shared__ float s_wts[kUpMaxTaps];
-  __shared__ int s_cnt;
+                          int chunks, int row_groups) {
+  // V as [col][half][cg] float4: the lanes of a warp store / load consecutive 16-byte words
+  extern __shared__ float4 s_v[];   // [2 * chunk_cols + kUpBwdHalo][2][CG]
+  __shared__ int s_roff[kUpBwdRows][kUpMaxTaps];     // element offset of the output row in its image
+  __shared__ float s_wts[kUpBwdRows][kUpMaxTaps];
+  __shared__ int s_cnt[kUpBwdRows];
+  __shared__ int s_ccnt[kUpBwdMaxCols];
+  __shared__ int s_ccol[kUpBwdMaxCols][kUpMaxTaps];     // staged column index (relative to ow_lo)
+  __shared__ float s_cwt[kUpBwdMaxCols][kUpMaxTaps];
   const int chunk = blockIdx.x % chunks;
-  const int row = blockIdx.x / chunks;
-  const int n = row / h;
-  const int hi = row - n * h;
+  const int rg = (blockIdx.x / chunks) % row_groups;
+  const int n = blockIdx.x / (chunks * row_groups);
+  const int hi0 = rg * kUpBwdRows;
+  const int nrows = min(kUpBwdRows, h - hi0);
   const int wi0 = chunk * chunk_cols;
   const int wi1 = min(w, wi0 + chunk_cols);
-  if (threadIdx.x == 0) {
-    int lo, hi_c, cnt = 0;
-    bilinear_candidates(hi, rh, h, lo, hi_c);
-    for (int oh = lo; oh <= hi_c && cnt < kUpMaxTaps; ++oh) {
-      const float wh = bilinear_weight(oh, rh, h, hi);
-      const int ph = oh + pad_top;
-      if (wh != 0.f && ph >= 0 && ph < Ho) { s_rows[cnt] = ph; s_wts[cnt] = wh; ++cnt; }
-    }
-    s_cnt = cnt;
-    // pad to a multiple of four taps (weight 0 on a row that is read anyway) so that the gather
-    // below always has four independent loads in flight
-    for (int t = cnt; t < kUpMaxTaps; ++t) { s_rows[t] = s_rows[0]; s_wts[t] = 0.f; }
-  }
-  __syncthreads();
-  const int cnt_h = s_cnt;
-  const int C = CG * 8;
   // output columns (upsampled coordinates) whose stencil can touch [wi0, wi1)
   int ow_lo, ow_hi, t0, t1;
   bilinear_candidates(wi0, rw, w, ow_lo, t0);
   bilinear_candidates(wi1 - 1, rw, w, t1, ow_hi);
   int ncols = ow_hi - ow_lo + 1;
   if (ncols > 2 * chunk_cols + kUpBwdHalo) ncols = 2 * chunk_cols + kUpBwdHalo;   // never (reach <= 3)
-  for (int i = threadIdx.x; i < ncols * CG; i += blockDim.x) {
-    const int col = i / CG;
-    const int cg = i - col * CG;
-    const int pw = ow_lo + col + pad_left;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (pw >= 0 && pw < Wo) {
-      const __nv_bfloat16* src = dout + ((long)n * Ho * Wo + pw) * lddo + cg * 8;
-      for (int t0 = 0; t0 < cnt_h; t0 += 4) {
-        uint4 q[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) q[t] = ld_stream(src + (long)s_rows[t0 + t] * Wo * lddo);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float g[8];
-          unpack8(q[t], g);
-          const float wt = s_wts[t0 + t];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, g[j], acc[j]);
-        }
-      }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // tap search, one candidate per lane (the candidate window is <= 10 wide, see
+  // bilinear_candidates); hits are compacted in candidate order with a ballot.
+  // rows: warp r handles source row hi0 + r
+  if (warp < nrows) {
+    const int hi = hi0 + warp;
+    int lo, hi_c, cnt = 0;
+    bilinear_candidates(hi, rh, h, lo, hi_c);
+    for (int b0 = lo; b0 <= hi_c; b0 += 32) {
+      const int oh = b0 + lane;
+      const float wh = oh <= hi_c ? bilinear_weight(oh, rh, h, hi) : 0.f;
+      const int ph = oh + pad_top;
+      const bool ok = wh != 0.f && ph >= 0 && ph < Ho;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (ok && pos < kUpMaxTaps) { s_roff[warp][pos] = ph * Wo * (int)lddo; s_wts[warp][pos] = wh; }
+      cnt = min(kUpMaxTaps, cnt + __popc(m));
     }
-    float4* dst = reinterpret_cast<float4*>(s_v + (long)col * C + cg * 8);
-    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    __syncwarp();
+    // pad to a multiple of four taps (weight 0 on a row that is read anyway) so that the gather
+    // below always has four independent loads in flight
+    if (lane >= cnt && lane < kUpMaxTaps) {
+      s_roff[warp][lane] = cnt > 0 ? s_roff[warp][0] : 0;
+      s_wts[warp][lane] = 0.f;
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
+  }
+  // columns: 8 lanes per source column of the chunk
+  {
+    const int grp = threadIdx.x >> 3, l8 = lane & 7;
+    constexpr int kGroups = kUpThreads / 8;
+    for (int wb = 0; wb < wi1 - wi0; wb += kGroups) {        // block-uniform trip count
+      const int wl = wb + grp;
+      const bool col_ok = wl < wi1 - wi0;
+      int c_lo = 0, c_hi = -1, cnt = 0;
+      if (col_ok) bilinear_candidates(wi0 + wl, rw, w, c_lo, c_hi);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {                        // window <= 16 candidates
+        const int ow = c_lo + it * 8 + l8;
+        const float ww = (col_ok && ow <= c_hi) ? bilinear_weight(ow, rw, w, wi0 + wl) : 0.f;
+        const int col = ow - ow_lo;
+        const bool ok = ww != 0.f && col >= 0 && col < ncols;
+        const unsigned m = (__ballot_sync(0xffffffffu, ok) >> (lane & 24)) & 0xffu;
+        const int pos = cnt + __popc(m & ((1u << l8) - 1u));
+        if (ok && pos < kUpMaxTaps) { s_ccol[wl][pos] = col; s_cwt[wl][pos] = ww; }
+        cnt = min(kUpMaxTaps, cnt + __popc(m));
+      }
+      if (col_ok && l8 == 0) s_ccnt[wl] = cnt;
+    }
   }
   __syncthreads();
-  __nv_bfloat16* drow = dx + (long)row * w * lddx;
-  for (int i = threadIdx.x; i < (wi1 - wi0) * CG; i += blockDim.x) {
-    const int wl = i / CG;
-    const int cg = i - wl * CG;
-    const int wi = wi0 + wl;
-    int c_lo, c_hi;
-    bilinear_candidates(wi, rw, w, c_lo, c_hi);
-    float acc[8];
+  const int cols_per_pass = kUpThreads / CG;
+  const int cg = threadIdx.x % CG;
+  const int col0 = threadIdx.x / CG;
+  const bool active = col0 < cols_per_pass;
+  const __nv_bfloat16* img = dout + (long)n * Ho * Wo * lddo + cg * 8;
+  const int ildo = (int)lddo;
+  for (int r = 0; r < nrows; ++r) {
+    const int cnt_h = s_cnt[r];
+    if (active) {
+      for (int col = col0; col < ncols; col += cols_per_pass) {
+        const int pw = ow_lo + col + pad_left;
+        float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int ow = c_lo; ow <= c_hi; ++ow) {
-      const float ww = bilinear_weight(ow, rw, w, wi);
-      const int col = ow - ow_lo;
-      if (ww == 0.f || col < 0 || col >= ncols) continue;
-      const float4* v = reinterpret_cast<const float4*>(s_v + (long)col * C + cg * 8);
-      const float4 a = v[0], b = v[1];
-      acc[0] = fmaf(ww, a.x, acc[0]); acc[1] = fmaf(ww, a.y, acc[1]);
-      acc[2] = fmaf(ww, a.z, acc[2]); acc[3] = fmaf(ww, a.w, acc[3]);
-      acc[4] = fmaf(ww, b.x, acc[4]); acc[5] = fmaf(ww, b.y, acc[5]);
-      acc[6] = fmaf(ww, b.z, acc[6]); acc[7] = fmaf(ww, b.w, acc[7]);
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        if (pw >= 0 && pw < Wo) {
+          const __nv_bfloat16* src = img + pw * ildo;
+          for (int t0 = 0; t0 < cnt_h; t0 += 4) {
+            uint4 q[4];
+#pragma unroll
+            // plain read-only loads: each output row is gathered by two source rows and the second
+            // read must hit L2 (ld_stream's L1::no_allocate marks the line evict-first in L2:
+            // measured 4.17 GB of DRAM reads for 2.15 GB of gradient)
+            for (int t = 0; t < 4; ++t) q[t] = __ldg(reinterpret_cast<const uint4*>(src + s_roff[r][t0 + t]));
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float g[8];
+              unpack8(q[t], g);
+              const float wt = s_wts[r][t0 + t];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, g[j], acc[j]);
+            }
+          }
+        }
+        s_v[(col * 2 + 0) * CG + cg] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        s_v[(col * 2 + 1) * CG + cg] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
     }
-    *reinterpret_cast<uint4*>(drow + (long)wi * lddx + cg * 8) = pack8(acc);
+    __syncthreads();
+    if (active) {
+      __nv_bfloat16* drow = dx + ((long)n * h + hi0 + r) * w * lddx + cg * 8;
+      for (int wl = col0; wl < wi1 - wi0; wl += cols_per_pass) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const int cnt = s_ccnt[wl];
+        for (int t = 0; t < cnt; ++t) {
+          const float ww = s_cwt[wl][t];
+          const int col = s_ccol[wl][t];
+          const float4 a = s_v[(col * 2 + 0) * CG + cg], b = s_v[(col * 2 + 1) * CG + cg];
+          acc[0] = fmaf(ww, a.x, acc[0]); acc[1] = fmaf(ww, a.y, acc[1]);
+          acc[2] = fmaf(ww, a.z, acc[2]); acc[3] = fmaf(ww, a.w, acc[3]);
+          acc[4] = fmaf(ww, b.x, acc[4]); acc[5] = fmaf(ww, b.y, acc[5]);
+          acc[6] = fmaf(ww, b.z, acc[6]); acc[7] = fmaf(ww, b.w, acc[7]);
+        }
+        *reinterpret_cast<uint4*>(drow + (long)(wi0 + wl) * lddx) = pack8(acc);
+      }
+    }
+    __syncthreads();   // V is overwritten by the next row
   }
 }
 
@@ -972,9 +1053,9 @@ static inline float align_corners_ratio(int in_size, int out_size) {
 
 int fpb200_upsample2x_pad_concat_fwd(const void* x, long ldx, void* out, long ldo, int N, int h,
                                      int w, int Ho, int Wo, int C, void* stream) {
-  if (C % 8 != 0 || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
+  if (C % 8 != 0 || C / 8 > kUpThreads || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
   const int pad_top = (Ho - 2 * h) / 2, pad_left = (Wo - 2 * w) / 2;
-  upsample2x_pad_fwd_kernel<<<N * ((Ho + kUpRows - 1) / kUpRows), 256, 0, (cudaStream_t)stream>>>(
+  upsample2x_pad_fwd_kernel<<<N * ((Ho + kUpRows - 1) / kUpRows), kUpThreads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, h, w, Ho, Wo, C / 8, pad_top,
       pad_left, align_corners_ratio(h, 2 * h), align_corners_ratio(w, 2 * w));
   return check_launch("upsample2x_pad_concat_fwd");
@@ -982,7 +1063,7 @@ int fpb200_upsample2x_pad_concat_fwd(const void* x, long ldx, void* out, long ld
 
 int fpb200_upsample2x_pad_concat_bwd(const void* dout, long lddo, void* dx, long lddx, int N,
                                      int h, int w, int Ho, int Wo, int C, void* stream) {
-  if (C % 8 != 0 || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
+  if (C % 8 != 0 || C / 8 > kUpThreads || Ho < 2 * h || Wo < 2 * w) return FPB200_ERR_SHAPE;
   const int pad_top = (Ho - 2 * h) / 2, pad_left = (Wo - 2 * w) / 2;
   const int chunk_cols = up_bwd_chunk_cols(C);
   const int chunks = (w + chunk_cols - 1) / chunk_cols;
@@ -994,10 +1075,13 @@ int fpb200_upsample2x_pad_concat_bwd(const void* dout, long lddo, void* dx, long
       return check_launch("upsample2x_pad_concat_bwd smem attribute");
     smem_set = 64 * 1024;
   }
-  if (smem > 64 * 1024) return FPB200_ERR_SHAPE;
-  upsample2x_pad_bwd_kernel<<<N * h * chunks, 256, smem, (cudaStream_t)stream>>>(
+  // 32-bit element offsets inside one image of dout
+  if (smem > 64 * 1024 || (long)Ho * Wo * lddo >= (1L << 31)) return FPB200_ERR_SHAPE;
+  const int row_groups = (h + kUpBwdRows - 1) / kUpBwdRows;
+  upsample2x_pad_bwd_kernel<<<N * row_groups * chunks, kUpThreads, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx, h, w, Ho, Wo, C / 8, pad_top,
-      pad_left, align_corners_ratio(h, 2 * h), align_corners_ratio(w, 2 * w), chunk_cols, chunks);
+      pad_left, align_corners_ratio(h, 2 * h), align_corners_ratio(w, 2 * w), chunk_cols, chunks,
+      row_groups);
   return check_launch("upsample2x_pad_concat_bwd");
 }
 

@@ -19,7 +19,8 @@ LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libfloodplanet_b200.so"
 INCLUDE = PKG_DIR.parent / "include"
 
-SOURCES = ["conv_igemm.cu", "conv_igemm_v1.cu", "conv_wgrad.cu", "elementwise.cu", "head_ce.cu", "fusion.cu"]
+SOURCES = ["conv_igemm.cu", "conv_igemm_v1.cu", "conv_wgrad.cu", "elementwise.cu", "head_ce.cu", "fusion.cu",
+           "augment.cu"]
 
 NVCC_FLAGS = [
     "-O3",

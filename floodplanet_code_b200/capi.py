@@ -58,6 +58,8 @@ SIGNATURES = {
     "fpb200_conv1x1_wgrad_bf16_nhwc": (_i, [_vp, _l, _vp, _l, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fpb200_channel_sum_rows": (_i, []),
     "fpb200_channel_sum_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _vp]),
+    "fpb200_augment_nchw_f32": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fpb200_plane_mean_std_f32": (_i, [_vp, _vp, _vp, _i, _l, _vp]),
     "fpb200_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
     "fpb200_adam_step_graphable": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _vp, _f, _vp]),
 }

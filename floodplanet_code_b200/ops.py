@@ -440,3 +440,53 @@ def canvas_to_mask_u8(canvas, weight, mask) -> None:
     st = _lib().fpb200_canvas_to_mask_u8(canvas.data_ptr(), weight.data_ptr(), mask.data_ptr(), h * w,
                                          canvas.shape[2], _stream())
     capi.check(st, "canvas_to_mask_u8", H=h, W=w, n_classes=canvas.shape[2])
+
+
+# ------------------------------------------------------------------------------------------
+def augment(image: torch.Tensor, target: Optional[torch.Tensor], theta: torch.Tensor, flags: torch.Tensor,
+            xgrid: torch.Tensor, ygrid: torch.Tensor, mean: Optional[torch.Tensor] = None,
+            std: Optional[torch.Tensor] = None, *, want_f32: bool = True, c_pad: int = 0):
+    """Fused normalise + hflip / vflip / rotate(nearest) gather over a batch (base_dataset.py:77-113,
+    532-555).  image fp32 NCHW, target int64 [N,H,W] or None; theta fp32 [N,6], flags int32 [N],
+    mean/std float64 [N,C] or None.  Returns (image fp32 NCHW | None, NHWC bf16 [N,H,W,c_pad] | None,
+    target int64 | None)."""
+    _require_cuda(image, target, theta, flags, xgrid, ygrid, mean, std)
+    if image.dim() != 4 or image.dtype != torch.float32:
+        raise RuntimeError(f"augment: image must be fp32 NCHW, got {image.dtype} {tuple(image.shape)}")
+    n, c, h, w = image.shape
+    image = image.contiguous()
+    if target is not None:
+        if target.dtype != torch.int64 or tuple(target.shape) != (n, h, w):
+            raise RuntimeError(f"augment: target must be int64 [N,H,W], got {target.dtype} {tuple(target.shape)}")
+        target = target.contiguous()
+    if tuple(theta.shape) != (n, 6) or theta.dtype != torch.float32 or tuple(flags.shape) != (n,) \
+            or flags.dtype != torch.int32 or xgrid.numel() != w or ygrid.numel() != h:
+        raise RuntimeError("augment: theta [N,6] fp32, flags [N] int32, xgrid [W], ygrid [H] expected")
+    if (mean is None) != (std is None):
+        raise RuntimeError("augment: mean and std go together")
+    if mean is not None and (mean.dtype != torch.float64 or std.dtype != torch.float64
+                             or mean.numel() != n * c or std.numel() != n * c):
+        raise RuntimeError("augment: mean / std must be float64 [N,C]")
+    out_f32 = torch.empty_like(image) if want_f32 else None
+    out_bf16 = torch.empty((n, h, w, c_pad), dtype=torch.bfloat16, device=image.device) if c_pad else None
+    tgt_out = torch.empty_like(target) if target is not None else None
+    st = _lib().fpb200_augment_nchw_f32(
+        image.data_ptr(), _ptr(out_f32), _ptr(out_bf16), c_pad, _ptr(target), _ptr(tgt_out),
+        theta.contiguous().data_ptr(), flags.contiguous().data_ptr(), xgrid.contiguous().data_ptr(),
+        ygrid.contiguous().data_ptr(), _ptr(mean.contiguous() if mean is not None else None),
+        _ptr(std.contiguous() if std is not None else None), n, c, h, w, _stream())
+    capi.check(st, "augment_nchw_f32", N=n, C=c, H=h, W=w, c_pad=c_pad)
+    return out_f32, out_bf16, tgt_out
+
+
+def plane_mean_std(image: torch.Tensor):
+    """Per-(sample, channel) mean and population std of an fp32 NCHW batch -> two float64 [N,C]."""
+    _require_cuda(image)
+    n, c, h, w = image.shape
+    image = image.contiguous()
+    mean = torch.empty((n, c), dtype=torch.float64, device=image.device)
+    std = torch.empty_like(mean)
+    st = _lib().fpb200_plane_mean_std_f32(image.data_ptr(), mean.data_ptr(), std.data_ptr(), n * c, h * w,
+                                          _stream())
+    capi.check(st, "plane_mean_std_f32", planes=n * c, hw=h * w)
+    return mean, std

@@ -292,6 +292,32 @@ int fpb200_channel_sum_bf16_nhwc(const void* x, long ld, float* partials, float*
                                  long num_pixels, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Per-sample normalise + augment on the device (datasets/base_dataset.py:77-113 `normalize`,
+ * :494-555 `sample_transforms` / `apply_transforms`; call order datasets/floodplanet.py:616-640)
+ * ---------------------------------------------------------------------------------------- */
+
+/* One gather pass: out[n,:,y,x] = normalise(img[n,:,src(y,x)]) with src = hflip o vflip o
+ * rotate(nearest, centre, fill 0) per sample, exactly torchvision's CPU index arithmetic.
+ *   img      fp32 NCHW [N,C,H,W]
+ *   out_f32  fp32 NCHW (the tensor the reference's DataLoader yields) and / or
+ *   out_nhwc_bf16  NHWC bf16 [N,H,W,c_pad] (channels >= C zero: the first conv's operand); either may be NULL
+ *   tgt / tgt_out  int64 [N,H,W] annotation, same geometric chain, fill 0 (both or neither)
+ *   theta    fp32 [N][6]: rows of theta^T / [W/2, H/2] = (x->gx, x->gy, y->gx, y->gy, 1->gx, 1->gy)
+ *   flags    int32 [N]: bit0 hflip, bit1 vflip, bit2 rotate
+ *   xgrid [W], ygrid [H]  fp32 base grid = linspace(-size/2 + .5, size/2 - .5, size)
+ *   mean / stdv  float64 [N][C] or both NULL: numpy `image -= mean; image /= std` on the fp32 image */
+int fpb200_augment_nchw_f32(const float* img, float* out_f32, void* out_nhwc_bf16, int c_pad,
+                            const int64_t* tgt, int64_t* tgt_out, const float* theta,
+                            const int* flags, const float* xgrid, const float* ygrid,
+                            const double* mean, const double* stdv, int N, int C, int H, int W,
+                            void* stream);
+
+/* norm_mode 'local' (base_dataset.py:98-104): mean and population std of each of the `planes`
+ * (= N*C) fp32 planes of hw pixels, rounded to fp32 like numpy's, stored as float64. */
+int fpb200_plane_mean_std_f32(const float* img, double* mean, double* stdv, int planes, long hw,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimiser (water_seg_model.py:198-205, optim.Adam defaults) and misc
  * ---------------------------------------------------------------------------------------- */
 

@@ -50,3 +50,17 @@ go = torch.ones((), device=dev)
 timeit("softmax_ce_bwd", lambda: ops.softmax_ce_bwd(logits, tgt, 0, res, go, dl), px * (12 + 8 + 12))
 img = torch.rand(N, 4, 512, 512, device=dev)
 timeit("ingest 4->16", lambda: ops.ingest([img], 16), px * (16 + 32))
+# normalise + augment gather (4 fp32 channels, int64 annotation), all three transforms on every sample
+from floodplanet_code_b200 import augment as G
+import numpy as np
+np.random.seed(0)
+cfg = {"hflip": {"active": True, "likelihood": 1.0}, "vflip": {"active": True, "likelihood": 1.0},
+       "rotate": {"active": True, "likelihood": 1.0, "min_rot_angle": 0, "max_rot_angle": 360}}
+aug = G.DeviceAugment(cfg, "global", {"mean": np.full(4, 0.4), "std": np.full(4, 0.2)})
+act = aug.sample(N)
+p = G.pack_params(act, 512, 512)
+th, fl, xg, yg = p["theta"].cuda(), p["flags"].cuda(), p["xgrid"].cuda(), p["ygrid"].cuda()
+mean, std = aug.normalize_stats(img)
+timeit("augment f32->f32 + target", lambda: ops.augment(img, tgt, th, fl, xg, yg, mean, std, want_f32=True), px * (16 + 16 + 8 + 8))
+timeit("augment f32->nhwc bf16 + target", lambda: ops.augment(img, tgt, th, fl, xg, yg, mean, std, want_f32=False, c_pad=16), px * (16 + 32 + 8 + 8))
+timeit("plane_mean_std (local norm)", lambda: ops.plane_mean_std(img), px * 16 * 2)

@@ -8,6 +8,7 @@ The GPU box has no /root/reference; tests there read only the fixtures.
 
     python tests/golden/make_golden.py          # everything
     python tests/golden/make_golden.py lf       # only the late-fusion fixture
+    python tests/golden/make_golden.py augment  # only the normalise / augment fixture
 """
 import importlib.util
 import sys
@@ -201,9 +202,75 @@ def lf_case(name, in_channels, n, h, w, n_classes, ignore_index, seed, block=8):
     print(name, "loss", float(loss.detach()), "bytes", (OUT / f"{name}.pt").stat().st_size)
 
 
+def augment_case():
+    """Outputs of the reference's OWN `BaseDataset.normalize / sample_transforms / apply_transforms`
+    (datasets/base_dataset.py:77-113,494-555), the class loaded by file path with stand-ins for the
+    modules that are not installed (tifffile, pytorch_lightning) or that only do file IO
+    (st_water_seg.datasets.utils); none of them touches the arithmetic under test."""
+    import numpy as np
+    tf = types.ModuleType("tifffile"); tf.tifffile = types.ModuleType("tifffile.tifffile")
+    sys.modules.setdefault("tifffile", tf); sys.modules.setdefault("tifffile.tifffile", tf.tifffile)
+    pl = types.ModuleType("pytorch_lightning"); pl.seed_everything = lambda s: None
+    sys.modules.setdefault("pytorch_lightning", pl)
+    for name in ("st_water_seg", "st_water_seg.datasets"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    du = types.ModuleType("st_water_seg.datasets.utils")
+    du.load_global_dataset_norm_params = lambda name: None
+    sys.modules["st_water_seg.datasets.utils"] = du
+    bd = load_by_path("ref_base_dataset", REF / "datasets" / "base_dataset.py")
+
+    class Cfg(dict):                         # attribute access like the OmegaConf node the reference reads
+        __getattr__ = dict.__getitem__
+
+    def cfg(h, v, r, lo=0, hi=360):
+        return Cfg(hflip=Cfg(active=True, likelihood=h), vflip=Cfg(active=True, likelihood=v),
+                   rotate=Cfg(active=True, likelihood=r, min_rot_angle=lo, max_rot_angle=hi))
+
+    cases = []
+    rng = np.random.RandomState(123)
+    specs = [  # (C, H, W, norm_mode, hflip p, vflip p, rotate p, numpy seed)
+        (4, 64, 64, None, 1.0, 0.0, 0.0, 1), (4, 64, 64, None, 0.0, 1.0, 0.0, 2),
+        (4, 64, 64, None, 0.0, 0.0, 1.0, 3), (4, 44, 36, "local", 1.0, 1.0, 1.0, 4),
+        (6, 75, 75, "global", 0.5, 0.5, 0.5, 5), (4, 75, 75, "local", 0.5, 0.5, 0.5, 6),
+        (2, 128, 128, None, 0.5, 0.5, 1.0, 7), (2, 37, 53, "global", 0.0, 1.0, 1.0, 8),
+        (1, 300, 300, None, 1.0, 0.0, 1.0, 9), (4, 64, 64, None, 0.0, 0.0, 0.0, 10),
+    ]
+    for (c, h, w, norm_mode, ph, pv, pr, seed) in specs:
+        ds = bd.BaseDataset.__new__(bd.BaseDataset)     # the methods under test read only these attributes
+        ds.norm_mode = norm_mode
+        ds.transforms = cfg(ph, pv, pr)
+        gp = None
+        if norm_mode == "global":
+            gp = {"mean": rng.rand(c), "std": rng.rand(c) + 0.5}       # float64, as np.mean / np.std of the sampled pixels give
+            ds.global_norm_params = {"PS": gp}
+        image = rng.rand(c, h, w).astype(np.float32)
+        target = (rng.rand(h, w) < 0.4).astype(np.int64)
+        np.random.seed(seed)
+        norm_image, mean, std = ds.normalize(image.copy(), "PS")
+        active = ds.sample_transforms()
+        out_img = ds.apply_transforms(norm_image, active, is_anno=False).float()
+        out_tgt = ds.apply_transforms(target, active, is_anno=True).long()
+        cases.append({
+            "image": torch.from_numpy(image), "target": torch.from_numpy(target).to(torch.int8), "norm_mode": norm_mode,
+            "global_params": None if gp is None else {k: torch.from_numpy(v) for k, v in gp.items()},
+            "cfg": {k: dict(v) for k, v in ds.transforms.items()}, "np_seed": seed,
+            "active": [{"transform": t["transform"].__name__, "kwargs": {k: float(v) for k, v in t["kwargs"].items()}}
+                       for t in active],
+            "mean": torch.as_tensor(np.asarray(mean)).flatten().double(),
+            "std": torch.as_tensor(np.asarray(std)).flatten().double(),
+            "out_image": out_img, "out_target": out_tgt.to(torch.int8),   # labels stored as int8 to keep the file small
+        })
+        print(f"augment case C{c} {h}x{w} norm={norm_mode}: active={[t['transform'].__name__ for t in active]}")
+    torch.save({"cases": cases, "torchvision": __import__("torchvision").__version__}, OUT / "augment.pt")
+    print(f"wrote {OUT / 'augment.pt'}")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lf":
         lf_case("lf_c4_dem1_32", {"ms_image": 4, "dem": 1}, n=2, h=32, w=32, n_classes=3, ignore_index=0, seed=11)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "augment":
+        augment_case()
         sys.exit(0)
     ref_unet = load_by_path("ref_unet", REF / "models" / "unet.py")
     unet_case(ref_unet, "unet_c4_32", n=2, c=4, h=32, w=32, n_classes=3, ignore_index=0, seed=0)
@@ -214,3 +281,4 @@ if __name__ == "__main__":
     op_semantics_case()
     tiler_case()
     lf_case("lf_c4_dem1_32", {"ms_image": 4, "dem": 1}, n=2, h=32, w=32, n_classes=3, ignore_index=0, seed=11)
+    augment_case()

@@ -301,7 +301,7 @@ def run_ours(args):
                        "training step at batch 64 (profiles/r01_traffic.json, ncu)")
     roofline = None
     if dom is not None:
-        kname = {"fprop": "conv3x3_igemm_kernel (fprop launches)", "dgrad": "conv3x3_igemm_kernel (dgrad launches)",
+        kname = {"fprop": "conv3x3_halo_kernel (fprop launches)", "dgrad": "conv3x3_halo_kernel (dgrad launches)",
                  "wgrad": "conv3x3_wgrad_kernel (+split-K reduce)"}[dom]
         roofline = {"bound": "tensor", "kernel": kname, "achieved": roof_all[dom]["achieved"], "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": roof_all[dom]["frac"], "traffic": traffic,

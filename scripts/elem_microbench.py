@@ -42,6 +42,10 @@ timeit("head1x1_fwd", lambda: ops.head1x1_fwd(x, w, b, logits), px * (128 + 12))
 dl = torch.randn(N, 3, 512, 512, device=dev); dx = torch.empty_like(x); dw = torch.empty(3, 64, device=dev); db = torch.empty(3, device=dev)
 parts = torch.empty(ops.head_bwd_rows(), 3 * 65, device=dev)
 timeit("head1x1_bwd", lambda: ops.head1x1_bwd(dl, x, w, dx, dw, db, parts), px * (128 + 128 + 12))
+sc64, sh64, mu64, is64 = f32(64) , f32(64) - 1.0, f32(64), f32(64)
+bnp = torch.zeros(ops.head_bwd_rows(), 2, 64, device=dev)
+timeit("head1x1_fwd (fused BN apply)", lambda: ops.head1x1_fwd(x, w, b, logits, sc64, sh64), px * (128 + 12))
+timeit("head1x1_bwd (fused BN apply+reduce)", lambda: ops.head1x1_bwd(dl, x, w, dx, dw, db, parts, bn=(sc64, sh64, mu64, is64), bn_partials=bnp), px * (128 + 128 + 12))
 tgt = (torch.rand(N, 512, 512, device=dev) < 0.42).long()
 res = torch.empty(4, dtype=torch.float64, device=dev); pred = torch.empty_like(tgt); conf = torch.zeros(3, 3, dtype=torch.int64, device=dev)
 cp = torch.empty(ops.ce_rows(), 4, dtype=torch.float64, device=dev)

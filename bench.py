@@ -131,7 +131,8 @@ def run_reference(args):
     if rank != 0:
         return
     sample = args.cpu_sample_batch
-    best, mean, cores, times = cpu_reference_chips_per_sec(sample, args.size, args.steps, args.warmup)
+    best, mean, cores, times = cpu_reference_chips_per_sec(sample, args.size, args.steps, args.warmup,
+                                                            args.channels)
     ms = 1000.0 * sum(times) / len(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": mean, "unit": UNIT, "n_gpus": args.gpus,
@@ -140,7 +141,7 @@ def run_reference(args):
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": mean, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"oracle port of the reference UNet+CE+Adam train step, fp32, {sample} chips "
-                                   f"of 4x{args.size}x{args.size} per step, {args.steps} steps after "
+                                   f"of {args.channels}x{args.size}x{args.size} per step, {args.steps} steps after "
                                    f"{args.warmup} warm-up (mean; best {best:.4f})"},
         "e2e": {"value": mean, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -150,12 +151,16 @@ def run_reference(args):
 
 def workload_config(args, world):
     return {
-        "workload": f"st_water_seg UNet (4->64..512..64->3, 17.27M params) bf16 train step on synthetic "
-                    f"4x{args.size}x{args.size} chips, masked CE ignore_index=0, Adam lr=1e-4",
-        "per_gpu_batch": args.batch, "global_batch": args.batch * world, "chip": [4, args.size, args.size],
+        "workload": (f"st_water_seg UNet ({args.channels}->64..512..64->3, 17.27M params) bf16 train step on synthetic "
+                     f"{args.channels}x{args.size}x{args.size} chips, masked CE ignore_index=0, Adam lr=1e-4"
+                     + ("" if args.channels == 4 else " (early fusion: PlanetScope + stacked extra sensor bands as a "
+                                                      "wide-input first conv, BASELINE configs[3])")),
+        "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+        "chip": [args.channels, args.size, args.size],
         "n_classes": N_CLASSES, "ignore_index": IGNORE_INDEX, "optimizer": "adam",
         "parallelism": f"dp{world}",
-        "l2": "inputs larger than L2: every step streams a fresh 268 MB image batch and >30 GB of "
+        "l2": f"inputs larger than L2: every step streams a fresh "
+              f"{args.batch * args.channels * args.size * args.size * 4 / 1e6:.0f} MB image batch and >30 GB of "
               "activations, far beyond the 126 MB L2",
     }
 
@@ -179,7 +184,7 @@ def run_ours(args):
     B, S = args.batch, args.size
 
     torch.manual_seed(0)
-    model = WaterSegmentationModel({"ms_image": 4}, N_CLASSES, LR, ignore_index=IGNORE_INDEX).to(dev)
+    model = WaterSegmentationModel({"ms_image": args.channels}, N_CLASSES, LR, ignore_index=IGNORE_INDEX).to(dev)
     broadcast_parameters(model)
     opt = FusedAdam(model.model, lr=LR)
     reducer = BucketedGradAllReduce(model.model) if world > 1 else None
@@ -189,7 +194,7 @@ def run_ours(args):
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = []
     for _ in range(args.pool):
-        img = torch.rand(B, 4, S, S, generator=g, device=dev)
+        img = torch.rand(B, args.channels, S, S, generator=g, device=dev)
         coarse = torch.rand(B, 1, S // 32, S // 32, generator=g, device=dev)
         tgt = (torch.nn.functional.interpolate(coarse, size=(S, S), mode="nearest")[:, 0] >= 0.58).long()
         pool.append({"image": img, "target": tgt})
@@ -367,10 +372,10 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        best, mean, cores, times = cpu_reference_chips_per_sec(args.cpu_sample_batch, S, 2, 1)
+        best, mean, cores, times = cpu_reference_chips_per_sec(args.cpu_sample_batch, S, 2, 1, args.channels)
         cpu_baseline = {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"oracle port of the reference UNet+CE+Adam train step (fp32, torch CPU), "
-                                  f"{args.cpu_sample_batch} chips of 4x{S}x{S}, 1 warm-up + best of 2 steps "
+                                  f"{args.cpu_sample_batch} chips of {args.channels}x{S}x{S}, 1 warm-up + best of 2 steps "
                                   f"({min(times):.2f} s/step)"}
 
     if rank == 0:
@@ -400,6 +405,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="chips per GPU per step")
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--channels", type=int, default=4,
+                    help="input bands: 4 = PlanetScope (headline); 16 = PS + S1 (2) + S2 (10) early fusion, configs[3]")
     ap.add_argument("--pool", type=int, default=2, help="distinct synthetic batches cycled through")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

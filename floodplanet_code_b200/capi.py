@@ -22,6 +22,7 @@ SIGNATURES = {
     "fpb200_ingest_scene_tiles": (_i, [_vp, _i, _l, _l, _vp, _i, _i, _i, _vp, _i, _vp]),
     "fpb200_repack_weights_fprop": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "fpb200_repack_weights_dgrad": (_i, [_vp, _vp, _i, _i, _vp]),
+    "fpb200_repack_weights_batch": (_i, [_vp, _i, _l, _vp]),
     "fpb200_conv_stat_rows": (_i, []),
     "fpb200_conv3x3_fprop_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "fpb200_conv3x3_pertap_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -138,6 +138,43 @@ __global__ void repack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// All 3x3 operand copies of a model in ONE launch (after an optimiser step every master weight
+// changed: 18 + 15 per-layer launches of a few microseconds each became one).  Each table entry
+// is one packed buffer = a contiguous range of blocks; kind 0 = fprop layout, 1 = dgrad layout.
+struct RepackEntry {
+  const float* w;        // fp32 OIHW master
+  __nv_bfloat16* out;    // packed copy
+  int cout, cin, cin_pad, kind;
+  long first_block;      // first block of this entry; entries are sorted by it
+};
+
+__global__ void __launch_bounds__(256)
+repack_batch_kernel(const RepackEntry* __restrict__ table, int n_entries) {
+  __shared__ int s_e;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < n_entries && table[e + 1].first_block <= (long)blockIdx.x) ++e;
+    s_e = e;
+  }
+  __syncthreads();
+  const RepackEntry en = table[s_e];
+  const long i = ((long)blockIdx.x - en.first_block) * blockDim.x + threadIdx.x;
+  if (en.kind == 0) {
+    if (i >= (long)en.cout * 9 * en.cin_pad) return;
+    const int ci = i % en.cin_pad;
+    const int tap = (i / en.cin_pad) % 9;
+    const int co = i / (9L * en.cin_pad);
+    const float v = ci < en.cin ? en.w[((long)co * en.cin + ci) * 9 + tap] : 0.f;
+    en.out[i] = __float2bfloat16(v);
+  } else {
+    if (i >= (long)en.cin * 9 * en.cout) return;
+    const int co = i % en.cout;
+    const int tap = (i / en.cout) % 9;
+    const int ci = i / (9L * en.cout);
+    en.out[i] = __float2bfloat16(en.w[((long)co * en.cin + ci) * 9 + (8 - tap)]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // BatchNorm statistics finalise (one warp per channel, fp64 accumulation)
 // ---------------------------------------------------------------------------
@@ -945,6 +982,14 @@ int fpb200_repack_weights_dgrad(const float* w_oihw, void* w_packed, int Cout, i
   repack_dgrad_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
       w_oihw, (__nv_bfloat16*)w_packed, Cout, Cin);
   return check_launch("repack_dgrad");
+}
+
+int fpb200_repack_weights_batch(const void* table, int n_entries, long total_blocks, void* stream) {
+  if (n_entries < 1 || total_blocks < 1 || total_blocks > 0x7fffffffL) return FPB200_ERR_SHAPE;
+  static_assert(sizeof(RepackEntry) == 40, "RepackEntry is mirrored field by field on the host");
+  repack_batch_kernel<<<(int)total_blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const RepackEntry*)table, n_entries);
+  return check_launch("repack_weights_batch");
 }
 
 int fpb200_bn_stats_finalize(const float* partials, int num_partials, int C, double count,

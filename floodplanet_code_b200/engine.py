@@ -110,6 +110,28 @@ class PackedWeights:
         # when True every lookup re-packs into the SAME buffer (CUDA-graph capture: the replayed
         # graph must contain the repack kernels because the optimiser changes the masters)
         self.always_repack = False
+        # one-launch refresh of every 3x3 copy: name -> (w, cin_pad) per table, device record array
+        self._meta: Dict[Tuple[int, str], Tuple[torch.Tensor, int]] = {}
+        self._batch = None          # (signature, table tensor, n_entries, total_blocks, [(table, name)])
+
+    def refresh_all(self) -> int:
+        """Re-pack every known 3x3 operand copy in ONE kernel launch and mark the copies current (the
+        fused Adam calls this right after its update: all masters changed).  Returns launches made."""
+        if self.always_repack or not self._meta:
+            return 0
+        items = sorted(self._meta.items())
+        tables = (self._fprop, self._dgrad)
+        sig = tuple((k, w.data_ptr(), tables[k[0]][k[1]][1].data_ptr()) for k, (w, _) in items)
+        if self._batch is None or self._batch[0] != sig:
+            entries = [(w, tables[k[0]][k[1]][1], cin_pad, k[0]) for k, (w, cin_pad) in items]
+            table, total = ops.repack_batch_table(entries, items[0][1][0].device)
+            self._batch = (sig, table, len(entries), total)
+        _, table, n, total = self._batch
+        ops.repack_batch(table, n, total)
+        for k, (w, _) in items:
+            tbl = tables[k[0]]
+            tbl[k[1]] = (self._key(w), tbl[k[1]][1])
+        return 1
 
     def invalidate(self) -> None:
         """For updates torch cannot see (raw-pointer kernels such as the fused Adam)."""
@@ -127,9 +149,11 @@ class PackedWeights:
         return table[name][1]
 
     def fprop(self, name: str, w: torch.Tensor, cin_pad: int) -> torch.Tensor:
+        self._meta[(0, name)] = (w, cin_pad)
         return self._lookup(self._fprop, name, w, lambda buf: ops.repack_fprop(w, cin_pad, buf))
 
     def dgrad(self, name: str, w: torch.Tensor) -> torch.Tensor:
+        self._meta[(1, name)] = (w, w.shape[1])
         return self._lookup(self._dgrad, name, w, lambda buf: ops.repack_dgrad(w, buf))
 
     def fprop_1x1(self, name: str, w: torch.Tensor) -> torch.Tensor:
@@ -175,6 +199,14 @@ class _Fwd:
         self.f32 = dict(dtype=torch.float32, device=dev)
         self.launches = 0
         self.stat_rows = ops.stat_rows()
+        self.nbt: List[torch.Tensor] = []      # num_batches_tracked counters bumped by this call
+
+    def flush_nbt(self) -> None:
+        """`num_batches_tracked += 1` of every BatchNorm run so far, as one multi-tensor op instead of
+        one tiny launch per layer."""
+        if self.nbt:
+            torch._foreach_add_(self.nbt, 1)
+            self.nbt = []
 
 
 class _Bwd:
@@ -286,7 +318,7 @@ class _Schedule:
             ops.bn_stats_finalize(parts, n * hh * ww, gamma, beta, bias, BN_EPS, BN_MOMENTUM,
                                   buffers[f"{s.bn}.running_mean"], buffers[f"{s.bn}.running_var"],
                                   scale, shift, mean, invstd)
-            buffers[f"{s.bn}.num_batches_tracked"].add_(1)
+            fw.nbt.append(buffers[f"{s.bn}.num_batches_tracked"])
             if defer_apply:
                 a = None
             elif pool_to is not None:
@@ -334,6 +366,7 @@ class _Schedule:
             cur = pooled
         cur = self._conv_bn_relu(fw, specs[li], specs[li].cin, cur, None, None, layers, pool_idx); li += 1
         cur = self._conv_bn_relu(fw, specs[li], specs[li].cin, cur, x5_view, None, layers, pool_idx)
+        fw.flush_nbt()
         return cur
 
     def _alloc_cat(self, fw: _Fwd) -> Dict[int, torch.Tensor]:
@@ -366,6 +399,7 @@ class _Schedule:
             else:
                 cur = self._conv_bn_relu(fw, specs[li], specs[li].cin, cur, None, None, layers, None)
             li += 1
+        fw.flush_nbt()
         if not head:
             return cur, None
         h, w = fw.sizes[0]

@@ -96,6 +96,24 @@ def repack_fprop(w: torch.Tensor, cin_pad: int, out: Optional[torch.Tensor] = No
     return out
 
 
+def repack_batch_table(entries, device) -> Tuple[torch.Tensor, int]:
+    """entries: [(w fp32 OIHW, packed bf16 buffer, cin_pad, kind)] -> (device table, total blocks) for
+    `repack_batch`; the record layout is the one documented in include/floodplanet_b200.h."""
+    import struct
+    blob, first = bytearray(), 0
+    for w, out, cin_pad, kind in entries:
+        cout, cin = w.shape[0], w.shape[1]
+        blob += struct.pack("<QQiiiiq", w.data_ptr(), out.data_ptr(), cout, cin, cin_pad, kind, first)
+        first += (out.numel() + 255) // 256
+    table = torch.frombuffer(blob, dtype=torch.uint8).clone().to(device)
+    return table, first
+
+
+def repack_batch(table: torch.Tensor, n_entries: int, total_blocks: int) -> None:
+    st = _lib().fpb200_repack_weights_batch(table.data_ptr(), n_entries, total_blocks, _stream())
+    capi.check(st, "repack_weights_batch", n_entries=n_entries, total_blocks=total_blocks)
+
+
 def repack_dgrad(w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _require_cuda(w)
     cout, cin = w.shape[0], w.shape[1]

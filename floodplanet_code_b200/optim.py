@@ -74,7 +74,8 @@ class FusedAdam:
         if slab is not None:
             ops.adam_step_graphable(self.flat, slab, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2,
                                     self.eps, self.step_state, grad_scale)
-            self.launches = 1
+            # every master weight just changed: refresh all bf16 operand copies in one launch
+            self.launches = 1 + self.unet._engine.packed.refresh_all()
             return
         self.step_count = int(self.step_state[0].item()) + 1
         # gradients came from somewhere else (e.g. accumulated): per-tensor launches

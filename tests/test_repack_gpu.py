@@ -1,0 +1,47 @@
+"""One-launch refresh of all packed bf16 weight copies (engine.PackedWeights.refresh_all, the batch
+repack kernel) must leave exactly the bytes the per-layer repack kernels produce, and training with the
+fused Adam must stay bit-identical to a run that re-packs layer by layer."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _train(steps, use_batch):
+    from floodplanet_code_b200.optim import FusedAdam
+    from floodplanet_code_b200.water_seg_model import WaterSegmentationModel
+    from oracle import unet_oracle as O
+    torch.manual_seed(0)
+    model = WaterSegmentationModel({"ms_image": 4}, 3, 1e-3, ignore_index=0)
+    model.model.load_state_dict(O.init_state_dict(4, 3, seed=0), strict=True)
+    model = model.cuda()
+    opt = FusedAdam(model.model, lr=1e-3)
+    packed = model.model._engine.packed
+    if not use_batch:
+        packed.refresh_all = lambda: 0          # fall back to lazy per-layer repacks at the next lookup
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 64, seed=1, block=8).items()}
+    losses = []
+    for i in range(steps):
+        opt.zero_grad()
+        loss = model.training_step(batch, i)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    nbt = model.model.inc.double_conv[1].num_batches_tracked.item()
+    return losses, {k: v.detach().clone() for k, v in model.model.state_dict().items()}, packed, opt, nbt
+
+
+def test_batch_repack_equals_per_layer_repack():
+    la, sa, pa, oa, nbt_a = _train(3, True)
+    lb, sb, pb, ob, nbt_b = _train(3, False)
+    assert la == lb and nbt_a == nbt_b == 3
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert oa.launches == 2 and ob.launches == 1
+    # after the last step the batch path has already refreshed every copy: compare with fresh packs
+    from floodplanet_code_b200 import ops
+    for (kind, name), (w, cin_pad) in pa._meta.items():
+        ref = ops.repack_fprop(w, cin_pad) if kind == 0 else ops.repack_dgrad(w)
+        got = (pa._fprop if kind == 0 else pa._dgrad)[name][1]
+        assert torch.equal(ref, got), (kind, name)
+    assert len(pa._meta) == 18 + 17          # 18 fprop copies, 17 dgrad copies (no dgrad into the image)

@@ -334,7 +334,13 @@ def test_bn_relu_backward(ops, n, h, w, c):
 
 
 @pytest.mark.parametrize("n,h,w,ho,wo,c", [(2, 8, 8, 16, 16, 64), (1, 18, 18, 37, 37, 128), (1, 1, 1, 2, 2, 64),
-                                           (1, 4, 5, 9, 10, 64)])
+                                           (1, 4, 5, 9, 10, 64),
+                                           # several column chunks and row groups of the backward, ragged last ones
+                                           (1, 20, 70, 40, 140, 64), (2, 37, 150, 75, 300, 64),
+                                           # 64 channel groups (4 columns per pass), padding on every side
+                                           (1, 9, 9, 21, 20, 512),
+                                           # channel-group counts that do not divide the block (idle threads)
+                                           (2, 11, 13, 22, 26, 24), (1, 75, 75, 151, 151, 8), (1, 6, 7, 12, 14, 192)])
 def test_upsample_pad_concat(ops, n, h, w, ho, wo, c):
     x = rand_act(n, h, w, c, 21)
     cat = torch.zeros(n, ho, wo, 2 * c, dtype=torch.bfloat16, device="cuda")

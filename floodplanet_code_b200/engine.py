@@ -251,6 +251,8 @@ class _Schedule:
         # from cross-stream allocator bookkeeping -- off by default.
         self.overlap_wgrad = False
         self._side_stream: Optional[torch.cuda.Stream] = None
+        self._fold_cache: Dict[str, Tuple[tuple, torch.Tensor, torch.Tensor]] = {}
+        self._bn_gen = 0
         self.launches = 0  # kernels launched by the last forward/backward (for bench accounting)
         self.names: List[str] = []
 
@@ -309,6 +311,7 @@ class _Schedule:
         shift = torch.empty(s.cout, **fw.f32)
         a = out_view if out_view is not None else torch.empty((n, hh, ww, s.cout), **fw.bf)
         if fw.training:
+            self._bn_gen += 1          # running statistics are about to be rewritten by a kernel
             y = torch.empty((n, hh, ww, s.cout), **fw.bf)
             parts = torch.empty((fw.stat_rows, 2, s.cout), **fw.f32)
             self._timed("fprop", s, n, hh * ww,
@@ -334,11 +337,22 @@ class _Schedule:
             if defer_apply:
                 return y, scale, shift
         else:
-            ops.bn_fold_eval(gamma, beta, bias, buffers[f"{s.bn}.running_mean"],
-                             buffers[f"{s.bn}.running_var"], BN_EPS, scale, shift)
+            # folded eval-mode coefficients are cached per layer until a parameter / running statistic
+            # can have changed: tensor version counters, plus the two generation counters that cover
+            # raw-pointer writers (fused Adam -> packed.generation, training-mode BatchNorm -> _bn_gen)
+            rm, rv = buffers[f"{s.bn}.running_mean"], buffers[f"{s.bn}.running_var"]
+            key = tuple((t._version, t.data_ptr()) for t in (gamma, beta, bias, rm, rv)) + (
+                self.packed.generation, self._bn_gen)
+            hit = self._fold_cache.get(s.bn)
+            if hit is not None and hit[0] == key:
+                scale, shift = hit[1], hit[2]
+            else:
+                ops.bn_fold_eval(gamma, beta, bias, rm, rv, BN_EPS, scale, shift)
+                self._fold_cache[s.bn] = (key, scale, shift)
+                fw.launches += 1
             self._timed("fprop", s, n, hh * ww,
                         lambda: ops.conv3x3_fprop(xin, wp, a, scale=scale, shift=shift, relu=True))
-            fw.launches += 2
+            fw.launches += 1
             if pool_to is not None:
                 idx = torch.empty(pool_to.shape, dtype=torch.uint8, device=dev)
                 ops.bn_apply_relu_maxpool2(a, None, pool_to, idx, None, None)

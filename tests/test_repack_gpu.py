@@ -45,3 +45,36 @@ def test_batch_repack_equals_per_layer_repack():
         got = (pa._fprop if kind == 0 else pa._dgrad)[name][1]
         assert torch.equal(ref, got), (kind, name)
     assert len(pa._meta) == 18 + 17          # 18 fprop copies, 17 dgrad copies (no dgrad into the image)
+
+
+def test_eval_fold_cache_tracks_training_updates():
+    """The cached eval-mode BatchNorm fold must be refreshed after anything that rewrites parameters or
+    running statistics through raw pointers (training-mode BatchNorm kernels, fused Adam)."""
+    from floodplanet_code_b200.optim import FusedAdam
+    from floodplanet_code_b200.unet import UNet
+    from floodplanet_code_b200.water_seg_model import WaterSegmentationModel
+    from oracle import unet_oracle as O
+    model = WaterSegmentationModel({"ms_image": 4}, 3, 1e-2, ignore_index=0)
+    model.model.load_state_dict(O.init_state_dict(4, 3, seed=0), strict=True)
+    model = model.cuda()
+    opt = FusedAdam(model.model, lr=1e-2)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 64, seed=1, block=8).items()}
+
+    def eval_logits(m):
+        m.eval()
+        with torch.no_grad():
+            return m(batch["image"]).clone()
+
+    e0 = eval_logits(model.model)
+    launches_first = model.model.kernel_launches
+    assert torch.equal(e0, eval_logits(model.model))                    # cache hit: same coefficients
+    assert model.model.kernel_launches == launches_first - 18          # 18 fold kernels skipped
+    for i in range(2):
+        opt.zero_grad()
+        model.training_step(batch, i).backward()
+        opt.step()
+    e1 = eval_logits(model.model)
+    assert not torch.equal(e0, e1)
+    fresh = UNet(4, 3)
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in model.model.state_dict().items()}, strict=True)
+    assert torch.equal(e1, eval_logits(fresh.cuda()))

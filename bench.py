@@ -189,6 +189,8 @@ def run_ours(args):
     opt = FusedAdam(model.model, lr=LR)
     reducer = BucketedGradAllReduce(model.model) if world > 1 else None
     engine = model.model._engine
+    if os.environ.get("FPB200_OVERLAP_WGRAD") == "1":   # experiment switch: wgrads on a second stream
+        engine.overlap_wgrad = True
 
     # synthetic data: U[0,1) image, blocky int64 target ~58% ignored / 42% flood
     g = torch.Generator(device=dev).manual_seed(1234 + rank)

@@ -72,9 +72,10 @@ constexpr int kPatch = 16;        // patch edge in pixels
 
 // TAPS = 9: 3x3 / pad 1 (box = patch + 1-pixel halo); TAPS = 1: pointwise (1x1) convolution,
 // the same pipeline with a halo-free 16 x 16 box and a single "tap".
-template <int BN, int KCH, int TAPS>
+template <int BN, int KCH, int TAPS, int EW = (BN >= 128 ? 4 : 8)>
 struct HaloCfg {
   static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
+  static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
   static constexpr int kHalo = TAPS == 9 ? 1 : 0;
   static constexpr int kBox = kPatch + 2 * kHalo;                   // box edge in pixels
   static constexpr int kBoxRows = kBox * kBox;
@@ -82,15 +83,16 @@ struct HaloCfg {
   static constexpr int kABytes = kBoxRows * kRowBytes;             // bytes the TMA writes
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;    // ring pitch
   static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kNB = BN >= 128 ? 5 : 8;                    // weight ring depth (<= 16)
-  // epilogue warps: one per (TMEM lane quadrant, MMA tile) when the MMAs are short (BN = 64:
-  // 32 tensor cycles each, the epilogue is co-critical), one per quadrant otherwise
-  static constexpr int kEpiWarps = BN >= 128 ? 4 : 8;
+  // epilogue warps: one per (TMEM lane quadrant, MMA tile) when the epilogue is co-critical
+  // (BN = 64: the MMAs are 32 tensor cycles each; BN = 128 with a single 64-channel K chunk: only
+  // 36 MMAs per tile pair), one per quadrant otherwise
+  static constexpr int kEpiWarps = EW;
+  static constexpr int kNB = BN >= 128 ? (EW == 8 ? 4 : 5) : 8;    // weight ring depth (<= 16)
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kStageOut = kEpiWarps * 4096;               // epilogue output staging, one 4 KB tile per warp
   // staging for the fused BatchNorm-backward reduction (dgrad): the y tile of the layer being
   // differentiated, TMA-loaded per (tile, unit); ping-pong when a warp walks several units
-  static constexpr int kYBufs = BN >= 128 ? 2 : 1;
+  static constexpr int kYBufs = (BN >= 128 && EW == 4) ? 2 : 1;
   static constexpr int kStageY = kEpiWarps * kYBufs * 4096;
   static constexpr int kBudget = 212 * 1024;
   static constexpr int kNARaw = (kBudget - kStageOut - kStageY - kNB * kBBytes) / kASlot;
@@ -103,12 +105,12 @@ struct HaloCfg {
   static_assert(4 * BN <= 512, "TMEM: 2 tiles x 2 stages x BN columns");
 };
 
-template <int BN, int KCH, int TAPS>
-__global__ void __launch_bounds__(HaloCfg<BN, KCH, TAPS>::kThreads, 1)
+template <int BN, int KCH, int TAPS, int EW = (BN >= 128 ? 4 : 8)>
+__global__ void __launch_bounds__(HaloCfg<BN, KCH, TAPS, EW>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYL,
                     const HaloParams p) {
-  using Cfg = HaloCfg<BN, KCH, TAPS>;
+  using Cfg = HaloCfg<BN, KCH, TAPS, EW>;
   constexpr int kNA = Cfg::kNA, kNB = Cfg::kNB;
   constexpr int kBox = Cfg::kBox, kHalo = Cfg::kHalo;
   constexpr uint32_t kRB = Cfg::kRowBytes;
@@ -401,6 +403,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             acc_sum[u][0] += s0; acc_sum[u][1] += s1;
             acc_sq[u][0] += q0; acc_sq[u][1] += q1;
+            if (Cfg::kYBufs == 1 && kUnitsPerItem > 1) {
+              // single y buffer, several units per item: fetch the next unit's tile once every lane
+              // has finished reading this one
+              const int k = tt * kUnits + u;
+              __syncwarp();
+              if (k + 1 < kUnitsPerItem) issue_y(k + 1);
+            }
           } else if (do_stats) {
             // lane l owns channels 2l, 2l+1 of this unit: walk the 32 staged rows
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -442,11 +451,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int KCH, int TAPS>
+template <int BN, int KCH, int TAPS, int EW = (BN >= 128 ? 4 : 8)>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                        const CUtensorMap& tmYL, const HaloParams& p, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN, KCH, TAPS>;
-  auto kern = conv3x3_halo_kernel<BN, KCH, TAPS>;
+  using Cfg = HaloCfg<BN, KCH, TAPS, EW>;
+  auto kern = conv3x3_halo_kernel<BN, KCH, TAPS, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
@@ -514,6 +523,13 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
                         stream) != cudaSuccess)
       return check_launch("conv3x3 stat memset");
   }
+  // one 64-channel K chunk under a 128-wide N tile: 36 MMAs per tile pair, so an epilogue that does
+  // more than convert (statistics or affine) is the critical path with 4 warps -> 8 epilogue warps,
+  // one per (quadrant, tile).  Measured (B = 64, 64 -> 128 @ 256^2 fprop with statistics): 0.619 ->
+  // 0.476 ms; with two or more K chunks the shallower rings of this variant cost more than the
+  // epilogue gains (128 -> 128: 0.834 -> 0.853 ms), and a plain dgrad epilogue has slack either way.
+  if (BN == 128 && KCH == 64 && taps == 9 && Cin == 64 && (p.stats_mode != 0 || scale != nullptr))
+    return launch_halo<128, 64, 9, 8>(tmA, tmB, tmY, tmYL, p, stream);
 #define FP_HALO_CASE(bn, kch, tp) \
   if (BN == bn && KCH == kch && taps == tp) return launch_halo<bn, kch, tp>(tmA, tmB, tmY, tmYL, p, stream);
   FP_HALO_CASE(128, 64, 9)

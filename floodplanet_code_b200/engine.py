@@ -501,7 +501,11 @@ class _Schedule:
                 # that layer's BatchNorm-backward reduction rides in this dgrad's epilogue.
                 # (Measured: pays off when the epilogue has slack -- 8 epilogue warps for
                 # 64-channel outputs, or >= 2304-deep GEMMs; for the 128-channel layers with
-                # short K the epilogue becomes critical and the separate pass is cheaper.)
+                # short K the epilogue becomes critical and the separate pass is cheaper.  Re-measured
+                # with the 8-epilogue-warp short-K variant: in isolation fusing wins for every second
+                # conv (128->64 @256^2: 0.69 vs 0.45 + 0.42 ms), inside the power-capped step it does
+                # not (dgrad family +1.0 ms for 1.06 ms of removed passes, 855 vs 857 chips/s at a
+                # higher clock), so the rule stays.)
                 ps, pv = prev
                 fparts = torch.empty((bw.stat_rows, 2, s.cin), **bw.f32)
                 self._timed("dgrad", s, n, hh * ww,

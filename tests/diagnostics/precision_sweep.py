@@ -1,4 +1,5 @@
-"""Diagnostic (GPU): distance of the CUDA path from (a) the fp32 oracle and (b) the oracle with
+"""Diagnostic (GPU, run by hand: `python tests/diagnostics/precision_sweep.py` from the repo root; lives under
+tests/ because it uses the oracle, which only test code may import): distance of the CUDA path from (a) the fp32 oracle and (b) the oracle with
 bf16 storage emulated, across problem sizes.  (b) isolates kernel bugs from bf16 rounding."""
 import copy, sys, torch
 sys.path.insert(0, '.')

@@ -320,6 +320,13 @@ __global__ void head_bwd_finalize_kernel(const float* __restrict__ partials, int
 // ---------------------------------------------------------------------------
 constexpr int kCeThreads = 256;
 
+// V pixels per thread (V = 4: 16-byte loads of each class plane, 2 x 16 bytes of int64 target and
+// prediction; V = 1 when hw is not a multiple of 4 or a pointer is not 16-byte aligned).  The confusion
+// counts are aggregated per warp with match_any (one shared-memory atomic per distinct (target,
+// prediction) pair and warp instead of one per pixel: with two live target classes the per-pixel
+// atomics were 32-way conflicts).  The loop trip count is block-uniform so that every lane takes part
+// in the warp votes.
+template <int V, int NC>
 __global__ void __launch_bounds__(kCeThreads)
 softmax_ce_argmax_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
                              long ignore_index, int64_t* __restrict__ pred,
@@ -331,47 +338,91 @@ softmax_ce_argmax_fwd_kernel(const float* __restrict__ logits, const int64_t* __
   __syncthreads();
   double loss_sum = 0.0;
   double cnt = 0.0, bad = 0.0;
-  const long total = (long)N * hw;
-  for (long px = blockIdx.x * (long)blockDim.x + threadIdx.x; px < total;
-       px += (long)gridDim.x * blockDim.x) {
-    const long n = px / hw, o = px - n * hw;
-    float l[kMaxClasses];
-    float best = 0.f;
-    int bi = 0;
+  const long groups = ((long)N * hw) / V;          // V divides hw
+  const long stride = (long)gridDim.x * blockDim.x;
+  const long iters = (groups + stride - 1) / stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long it = 0; it < iters; ++it) {
+    const long gi = it * stride + blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const bool in = gi < groups;
+    const long px = gi * V;
+    const long n = in ? px / hw : 0, o = in ? px - n * hw : 0;
+    float l[NC][V];
+    int64_t t[V];
+    if (in) {
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
-      if (k < ncls) {
-        l[k] = __ldg(logits + ((long)n * ncls + k) * hw + o);
-        // first maximum wins; NaN counts as the maximum (torch.argmax semantics)
-        if (k == 0 || (l[k] > best) || (l[k] != l[k] && best == best)) { best = l[k]; bi = k; }
-      }
-    }
-    const long t = target[px];
-    if (pred != nullptr) pred[px] = bi;
-    if (t != ignore_index) {
-      if (t < 0 || t >= ncls) {
-        bad += 1.0;
-      } else {
-        float mx = l[0];
-#pragma unroll
-        for (int k = 1; k < kMaxClasses; ++k)
-          if (k < ncls) mx = fmaxf(mx, l[k]);
-        float se = 0.f, lt = 0.f;
-#pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) {
-          if (k < ncls) {
-            se += expf(l[k] - mx);
-            if (k == (int)t) lt = l[k];
+      for (int k = 0; k < NC; ++k) {
+        if (k < ncls) {
+          const float* src = logits + ((long)n * ncls + k) * hw + o;
+          if (V == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+            l[k][0] = v.x; l[k][1 % V] = v.y; l[k][2 % V] = v.z; l[k][3 % V] = v.w;
+          } else {
+            l[k][0] = __ldg(src);
           }
         }
-        loss_sum += (double)((mx + logf(se)) - lt);
-        cnt += 1.0;
-        if (confusion != nullptr) atomicAdd(&s_conf[(int)t * kMaxClasses + bi], 1u);
+      }
+      if (V == 4) {
+        const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(target + px));
+        const longlong2 b2 = __ldg(reinterpret_cast<const longlong2*>(target + px) + 1);
+        t[0] = a.x; t[1 % V] = a.y; t[2 % V] = b2.x; t[3 % V] = b2.y;
+      } else {
+        t[0] = target[px];
+      }
+    }
+    int64_t pv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      int key = -1;
+      if (in) {
+        float best = 0.f;
+        int bi = 0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          if (k < ncls) {
+            // first maximum wins; NaN counts as the maximum (torch.argmax semantics)
+            if (k == 0 || (l[k][j] > best) || (l[k][j] != l[k][j] && best == best)) { best = l[k][j]; bi = k; }
+          }
+        }
+        pv[j] = bi;
+        if (t[j] != ignore_index) {
+          if (t[j] < 0 || t[j] >= ncls) {
+            bad += 1.0;
+          } else {
+            float mx = l[0][j];
+#pragma unroll
+            for (int k = 1; k < NC; ++k)
+              if (k < ncls) mx = fmaxf(mx, l[k][j]);
+            float se = 0.f, lt = 0.f;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+              if (k < ncls) {
+                se += expf(l[k][j] - mx);
+                if (k == (int)t[j]) lt = l[k][j];
+              }
+            }
+            loss_sum += (double)((mx + logf(se)) - lt);
+            cnt += 1.0;
+            key = (int)t[j] * kMaxClasses + bi;
+          }
+        }
+      }
+      if (confusion != nullptr) {
+        const unsigned same = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && lane == __ffs(same) - 1) atomicAdd(&s_conf[key], (unsigned)__popc(same));
+      }
+    }
+    if (in && pred != nullptr) {
+      if (V == 4) {
+        longlong2* dst = reinterpret_cast<longlong2*>(pred + px);
+        dst[0] = make_longlong2(pv[0], pv[1 % V]);
+        dst[1] = make_longlong2(pv[2 % V], pv[3 % V]);
+      } else {
+        pred[px] = pv[0];
       }
     }
   }
   // block reduce
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
     loss_sum += __shfl_xor_sync(0xffffffffu, loss_sum, o);
@@ -417,6 +468,7 @@ __global__ void ce_finalize_kernel(const double* __restrict__ partials, int P, d
   }
 }
 
+template <int V, int NC>
 __global__ void __launch_bounds__(kCeThreads)
 softmax_ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
                       long ignore_index, const double* __restrict__ result,
@@ -425,31 +477,60 @@ softmax_ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restric
   const double count = result[1];
   const float go = grad_out != nullptr ? __ldg(grad_out) : 1.f;
   const float coef = count > 0.0 ? go / (float)count : 0.f;
-  const long total = (long)N * hw;
-  for (long px = blockIdx.x * (long)blockDim.x + threadIdx.x; px < total;
-       px += (long)gridDim.x * blockDim.x) {
+  const long groups = ((long)N * hw) / V;
+  for (long gi = blockIdx.x * (long)blockDim.x + threadIdx.x; gi < groups;
+       gi += (long)gridDim.x * blockDim.x) {
+    const long px = gi * V;
     const long n = px / hw, o = px - n * hw;
-    const long t = target[px];
-    const bool active = (t != ignore_index) && t >= 0 && t < ncls && coef != 0.f;
-    float l[kMaxClasses];
-    float mx = -INFINITY;
+    int64_t t[V];
+    if (V == 4) {
+      const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(target + px));
+      const longlong2 b2 = __ldg(reinterpret_cast<const longlong2*>(target + px) + 1);
+      t[0] = a.x; t[1 % V] = a.y; t[2 % V] = b2.x; t[3 % V] = b2.y;
+    } else {
+      t[0] = target[px];
+    }
+    bool active[V], any = false;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
+    for (int j = 0; j < V; ++j) {
+      active[j] = (t[j] != ignore_index) && t[j] >= 0 && t[j] < ncls && coef != 0.f;
+      any |= active[j];
+    }
+    float l[NC][V];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
       if (k < ncls) {
-        l[k] = active ? __ldg(logits + ((long)n * ncls + k) * hw + o) : 0.f;
-        mx = fmaxf(mx, l[k]);
+        const float* src = logits + ((long)n * ncls + k) * hw + o;
+        if (V == 4) {
+          // logits of fully ignored groups are not read at all (58 % of the default labels)
+          const float4 v = any ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          l[k][0] = v.x; l[k][1 % V] = v.y; l[k][2 % V] = v.z; l[k][3 % V] = v.w;
+        } else {
+          l[k][0] = any ? __ldg(src) : 0.f;
+        }
       }
     }
-    float se = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
-      if (k < ncls) { l[k] = expf(l[k] - mx); se += l[k]; }
-    const float inv = 1.f / se;
+    for (int j = 0; j < V; ++j) {
+      float mx = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
+      for (int k = 0; k < NC; ++k)
+        if (k < ncls) { if (!active[j]) l[k][j] = 0.f; mx = fmaxf(mx, l[k][j]); }
+      float se = 0.f;
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+        if (k < ncls) { l[k][j] = expf(l[k][j] - mx); se += l[k][j]; }
+      const float inv = 1.f / se;
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+        if (k < ncls) l[k][j] = active[j] ? (l[k][j] * inv - (k == (int)t[j] ? 1.f : 0.f)) * coef : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
       if (k < ncls) {
-        const float g = active ? (l[k] * inv - (k == (int)t ? 1.f : 0.f)) * coef : 0.f;
-        dlogits[((long)n * ncls + k) * hw + o] = g;
+        float* dst = dlogits + ((long)n * ncls + k) * hw + o;
+        if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(l[k][0], l[k][1 % V], l[k][2 % V], l[k][3 % V]);
+        else dst[0] = l[k][0];
       }
     }
   }
@@ -575,12 +656,18 @@ int fpb200_softmax_ce_argmax_fwd(const float* logits, const int64_t* target, lon
                                  double* partials, int N, int n_classes, long hw, void* stream) {
   if (n_classes < 1 || n_classes > kMaxClasses || N < 1 || hw < 1) return FPB200_ERR_SHAPE;
   const long total = (long)N * hw;
-  long g = (total + kCeThreads - 1) / kCeThreads;
+  const bool vec = hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(target) |
+                                    reinterpret_cast<uintptr_t>(pred)) & 15) == 0;
+  long g = (total / (vec ? 4 : 1) + kCeThreads - 1) / kCeThreads;
   const int rows = fpb200_ce_rows();
   if (g > rows) g = rows;
-  softmax_ce_argmax_fwd_kernel<<<(int)g, kCeThreads, 0, (cudaStream_t)stream>>>(
-      logits, target, ignore_index, pred, (unsigned long long*)confusion, partials, N, n_classes,
-      hw);
+#define FP_CE_FWD(v, nc)                                                                          \
+  softmax_ce_argmax_fwd_kernel<v, nc><<<(int)g, kCeThreads, 0, (cudaStream_t)stream>>>(             \
+      logits, target, ignore_index, pred, (unsigned long long*)confusion, partials, N, n_classes, hw)
+  if (vec && n_classes <= 4) FP_CE_FWD(4, 4);
+  else if (vec) FP_CE_FWD(4, kMaxClasses);
+  else FP_CE_FWD(1, kMaxClasses);
+#undef FP_CE_FWD
   int rc = check_launch("softmax_ce_argmax_fwd");
   if (rc != FPB200_OK) return rc;
   ce_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, (int)g, result);
@@ -592,10 +679,17 @@ int fpb200_softmax_ce_bwd(const float* logits, const int64_t* target, long ignor
                           int n_classes, long hw, void* stream) {
   if (n_classes < 1 || n_classes > kMaxClasses) return FPB200_ERR_SHAPE;
   const long total = (long)N * hw;
-  long g = (total + kCeThreads - 1) / kCeThreads;
+  const bool vec = hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(target) |
+                                    reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0;
+  long g = (total / (vec ? 4 : 1) + kCeThreads - 1) / kCeThreads;
   if (g > 148L * 16) g = 148L * 16;
-  softmax_ce_bwd_kernel<<<(int)g, kCeThreads, 0, (cudaStream_t)stream>>>(
-      logits, target, ignore_index, result, grad_out, dlogits, N, n_classes, hw);
+#define FP_CE_BWD(v, nc)                                                                          \
+  softmax_ce_bwd_kernel<v, nc><<<(int)g, kCeThreads, 0, (cudaStream_t)stream>>>(                    \
+      logits, target, ignore_index, result, grad_out, dlogits, N, n_classes, hw)
+  if (vec && n_classes <= 4) FP_CE_BWD(4, 4);
+  else if (vec) FP_CE_BWD(4, kMaxClasses);
+  else FP_CE_BWD(1, kMaxClasses);
+#undef FP_CE_BWD
   return check_launch("softmax_ce_bwd");
 }
 

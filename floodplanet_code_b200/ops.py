@@ -104,7 +104,9 @@ def repack_batch_table(entries, device) -> Tuple[torch.Tensor, int]:
     for w, out, cin_pad, kind in entries:
         cout, cin = w.shape[0], w.shape[1]
         blob += struct.pack("<QQiiiiq", w.data_ptr(), out.data_ptr(), cout, cin, cin_pad, kind, first)
-        first += (out.numel() + 255) // 256
+        first += cout if kind == 0 else cin      # one block per output (fprop) / input (dgrad) channel
+        if cin > 1024:
+            raise RuntimeError(f"repack_batch: Cin {cin} exceeds the 1024 channels the batch kernel stages")
     table = torch.frombuffer(blob, dtype=torch.uint8).clone().to(device)
     return table, first
 

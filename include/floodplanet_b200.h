@@ -67,8 +67,9 @@ int fpb200_repack_weights_dgrad(const float* w_oihw, void* w_packed, int Cout, i
 /* Every 3x3 operand copy of a model in one launch (what an optimiser step invalidates).
  * table: device array of n_entries records, 40 bytes each, sorted by first_block:
  *   { const float* w_oihw; void* packed; int32 cout, cin, cin_pad, kind (0 fprop layout, 1 dgrad
- *     layout); int64 first_block }   -- entry e owns blocks [first_block[e], first_block[e+1]) of 256
- *   elements of its packed buffer; total_blocks = end of the last entry. */
+ *     layout); int64 first_block }   -- entry e owns blocks [first_block[e], first_block[e+1]): one block
+ *   per output channel (kind 0) or per input channel (kind 1); cin <= 1024; total_blocks = end of the
+ *   last entry. */
 int fpb200_repack_weights_batch(const void* table, int n_entries, long total_blocks, void* stream);
 
 /* ------------------------------------------------------------------------------------------

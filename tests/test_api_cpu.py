@@ -165,3 +165,20 @@ def test_encoder_decoder_halves_share_unet_names():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         from floodplanet_code_b200.unet import UNet
         UNet(4, 3).encode(torch.zeros(1, 4, 32, 32))
+
+
+def test_repack_batch_table_layout():
+    """The host-built record array of `fpb200_repack_weights_batch` (include/floodplanet_b200.h): 40-byte
+    records {w ptr, packed ptr, cout, cin, cin_pad, kind, first_block}, one block per output channel
+    (fprop layout) or per input channel (dgrad layout), sorted by first_block."""
+    import struct
+    import torch
+    from floodplanet_code_b200 import ops
+    w1, w2 = torch.zeros(8, 4, 3, 3), torch.zeros(16, 8, 3, 3)
+    o1 = torch.zeros(8, 9, 16, dtype=torch.bfloat16)
+    o2 = torch.zeros(8, 9, 16, dtype=torch.bfloat16)
+    table, total = ops.repack_batch_table([(w1, o1, 16, 0), (w2, o2, 8, 1)], "cpu")
+    assert table.numel() == 2 * 40 and total == 8 + 8
+    recs = [struct.unpack_from("<QQiiiiq", bytes(table.numpy().tobytes()), 40 * i) for i in range(2)]
+    assert recs[0] == (w1.data_ptr(), o1.data_ptr(), 8, 4, 16, 0, 0)
+    assert recs[1] == (w2.data_ptr(), o2.data_ptr(), 16, 8, 8, 1, 8)

@@ -29,6 +29,12 @@
 //                  offset inside the same box; B = x, unshifted.  5 pairs cover the 9 taps.
 //   MODE_POINTWISE (1x1 convolution, the late-fusion concat_convs): no halo, one tap:
 //                  A = 128 output channels of dy, B = NB blocks of 64 input channels of x.
+//   MODE_X_STACK  (Cout == 64 blocks with < 64 input channels, i.e. the first layer): with N = 16
+//                  an M128 MMA is 8 tensor cycles of work for 4.5 KB of operands, and MODE_DY_SHIFT
+//                  re-reads the dy operand for each of its 20 MMAs per stage (90 KB, shared-memory
+//                  bound at 17 % tensor-pipe utilisation, ncu).  Here A = dy unshifted (M = 64),
+//                  B = x box with halo, and the three taps of a filter row are stacked on N
+//                  (N blocks one pixel apart, LBO = one pixel row): 12 MMAs and 42 KB per stage.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -56,19 +62,20 @@ template <int MODE, int NBW, int NB>
 struct WgCfg {
   // A = dy.  mode 0: two [64 px][64 co] blocks; mode 1: one haloed box 18 x 6 px (padded slot)
   static constexpr int kABlock = MODE != 1 ? kWgBK * 128 : kWgBoxW * (kWgTH + 2) * 128;
-  static constexpr int kABytes = MODE != 1 ? 2 * kABlock : kABlock;          // TMA bytes
+  static constexpr int kABytes = (MODE == 0 || MODE == 2) ? 2 * kABlock : kABlock;          // TMA bytes
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024 + (MODE != 1 ? 0 : 1024);
   // B = x.  mode 0: NB blocks of one filter row with halo [18 x 4 px][64 ci]; mode 1: [64 px][NBW];
   // mode 2: NB blocks [64 px][64 ci]
-  static constexpr int kBBlock = MODE == 0 ? kWgBoxW * kWgTH * 128 : kWgBK * NBW * 2;
-  static constexpr int kBBytes = MODE != 1 ? NB * kBBlock : kBBlock;
+  static constexpr int kBBlock = MODE == 0 ? kWgBoxW * kWgTH * 128
+                               : (MODE == 3 ? kWgBoxW * (kWgTH + 2) * NBW * 2 : kWgBK * NBW * 2);
+  static constexpr int kBBytes = (MODE == 0 || MODE == 2) ? NB * kBBlock : kBBlock;
   static constexpr int kBSlot = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kASlot + kBSlot;
   static constexpr int kTxBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kGroups = MODE == 0 ? 3 : (MODE == 1 ? 5 : 1);
-  static constexpr int kN = NBW * NB;                     // UMMA N per group
+  static constexpr int kGroups = (MODE == 0 || MODE == 3) ? 3 : (MODE == 1 ? 5 : 1);
+  static constexpr int kN = MODE == 3 ? 3 * NBW : NBW * NB;   // UMMA N per group
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -85,8 +92,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
                      const WgradParams p) {
   using Cfg = WgCfg<MODE, NBW, NB>;
   constexpr int kStages = Cfg::kStages;
-  constexpr uint32_t kIdesc = make_idesc_bf16(128, Cfg::kN, 1, 1);
-  constexpr uint32_t kBRow = MODE != 1 ? 128 : NBW * 2;   // bytes per pixel row of B
+  constexpr uint32_t kIdesc = make_idesc_bf16(MODE == 3 ? 64 : 128, Cfg::kN, 1, 1);
+  constexpr uint32_t kBRow = (MODE == 0 || MODE == 2) ? 128 : NBW * 2;   // bytes per pixel row of B
   constexpr uint32_t kBSwz = kBRow;
   constexpr uint32_t kBSBO = 8 * kBRow;
 
@@ -108,11 +115,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   const int r_idx = item % p.items_r;
   const int ci_grp = (item / p.items_r) % p.items_ci;
   const int co_grp = item / (p.items_r * p.items_ci);
-  const int co0 = co_grp * (MODE != 1 ? 128 : 64);
+  const int co0 = co_grp * ((MODE == 0 || MODE == 2) ? 128 : 64);
   // second 64-channel block of A; a 64-channel pointwise layer re-reads the first block (its
   // duplicate accumulator rows are discarded)
   const int co1 = (MODE == 2 && co0 + 64 >= p.Cout) ? co0 : co0 + 64;
-  const int ci0 = ci_grp * Cfg::kN;
+  const int ci0 = ci_grp * (MODE == 3 ? NBW : Cfg::kN);
   const int t_begin = (int)(((long)p.num_pix_tiles * split) / p.ksplit);
   const int t_end = (int)(((long)p.num_pix_tiles * (split + 1)) / p.ksplit);
 
@@ -161,6 +168,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 #pragma unroll
           for (int b = 0; b < NB; ++b)
             tma_load_4d(sb + b * Cfg::kBBlock, &tmX, full_bar(stage), ci0 + b * 64, w0, h0, img);
+        } else if (MODE == 3) {
+          tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0, h0, img);
+          tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0 - 1, h0 - 1, img);
         } else {
           tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0 - 1, h0 - 1, img);
           tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0, h0, img);
@@ -198,6 +208,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
             } else if (MODE == 2) {
               a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
               b_lo = (b_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kBBlock) >> 4) << 16);
+            } else if (MODE == 3) {
+              // A: dy row k of the tile, one 64-channel block.  B: x row k + r of the haloed box
+              // (r = g), the three taps s = 0..2 as N blocks one pixel row (kBRow bytes) apart
+              a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
+              b_lo = (b_addr16 + ((((k + g) * kWgBoxW) * kBRow) >> 4)) | ((kBRow >> 4) << 16);
             } else {
               // A: haloed dy box; first M block at the pair's first tap, second block LBO further
               a_lo = (a_addr16 + (((k * kWgBoxW + wg_pair_offset(g)) * 128) >> 4)) |
@@ -224,7 +239,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 #pragma unroll
     for (int g = 0; g < Cfg::kGroups; ++g) {
       int co, tap;
-      if (MODE == 0) {
+      if (MODE == 3) {
+        // M = 64 accumulator: rows 16q .. 16q+15 live in lanes 0..15 of TMEM lane quadrant q
+        co = co0 + quad * 16 + (lane & 15);
+        tap = lane < 16 ? g * 3 : -1;   // + s per column chunk below
+      } else if (MODE == 0) {
         co = co0 + row;
         tap = r_idx * 3 + g;
       } else if (MODE == 2) {
@@ -241,7 +260,21 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         uint32_t r[16];
         tmem_ld_32x16(tmem_base + (uint32_t(quad * 32) << 16) + g * Cfg::kN + c * 16, r);
         tmem_ld_wait();
-        if (tap >= 0) {
+        if (MODE == 3) {
+          // column chunk c = tap s = (16 c) / NBW, channels (16 c) % NBW ..
+          if (tap >= 0) {
+            float* d3 = ws + ((size_t)co * p.taps + tap + (c * 16) / NBW) * p.Cin + ci0 + (c * 16) % NBW;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 o;
+              o.x = have ? __uint_as_float(r[q * 4 + 0]) : 0.f;
+              o.y = have ? __uint_as_float(r[q * 4 + 1]) : 0.f;
+              o.z = have ? __uint_as_float(r[q * 4 + 2]) : 0.f;
+              o.w = have ? __uint_as_float(r[q * 4 + 3]) : 0.f;
+              *reinterpret_cast<float4*>(d3 + q * 4) = o;
+            }
+          }
+        } else if (tap >= 0) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float4 o;
@@ -300,6 +333,12 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl, int ta
     pl->items_r = 3;
     pl->items_ci = Cin / (64 * pl->nb);
     pl->n_items = (Cout / 128) * pl->items_ci * 3;
+  } else if (Cin % 64 != 0) {
+    pl->mode = 3; pl->nb = 1;
+    pl->nbw = (Cin % 32 == 0) ? 32 : 16;
+    pl->items_r = 1;
+    pl->items_ci = Cin / pl->nbw;
+    pl->n_items = (Cout / 64) * pl->items_ci;
   } else {
     pl->mode = 1; pl->nb = 1;
     pl->nbw = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
@@ -371,6 +410,10 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
     rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgTW, kWgTH);
     if (rc != FPB200_OK) return rc;
     rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, 64, kWgBoxW, kWgTH);
+  } else if (pl.mode == 3) {
+    rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgTW, kWgTH);
+    if (rc != FPB200_OK) return rc;
+    rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, pl.nbw, kWgBoxW, kWgTH + 2);
   } else {
     rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgBoxW, kWgTH + 2);
     if (rc != FPB200_OK) return rc;
@@ -386,6 +429,8 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
   p.ws = reinterpret_cast<float*>(workspace);
   if (pl.mode == 0 && pl.nb == 2) rc = launch_wgrad<0, 64, 2>(tmDY, tmX, p, stream);
   else if (pl.mode == 0) rc = launch_wgrad<0, 64, 1>(tmDY, tmX, p, stream);
+  else if (pl.mode == 3 && pl.nbw == 32) rc = launch_wgrad<3, 32, 1>(tmDY, tmX, p, stream);
+  else if (pl.mode == 3) rc = launch_wgrad<3, 16, 1>(tmDY, tmX, p, stream);
   else if (pl.nbw == 64) rc = launch_wgrad<1, 64, 1>(tmDY, tmX, p, stream);
   else if (pl.nbw == 32) rc = launch_wgrad<1, 32, 1>(tmDY, tmX, p, stream);
   else rc = launch_wgrad<1, 16, 1>(tmDY, tmX, p, stream);

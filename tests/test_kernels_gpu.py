@@ -150,6 +150,9 @@ WGRAD_SHAPES = [
     (2, 16, 16, 64, 64, 64),      # MODE_DY_SHIFT, 64
     (2, 16, 16, 16, 4, 64),       # first layer (pad 16)
     (1, 16, 16, 32, 21, 64),      # early fusion pad 32
+    (1, 37, 29, 16, 6, 64),       # MODE_X_STACK: odd size (ragged tiles, halo beyond the image)
+    (2, 20, 24, 48, 40, 64),      # MODE_X_STACK: three 16-channel input blocks
+    (1, 16, 32, 16, 16, 128),     # MODE_X_STACK: two 64-channel output blocks
     (1, 37, 37, 128, 128, 64),    # odd size, Cout 64 / Cin 128
     (3, 18, 18, 256, 256, 512),
     (1, 64, 64, 64, 64, 64),

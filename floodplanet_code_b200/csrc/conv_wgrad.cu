@@ -29,6 +29,13 @@
 //                  offset inside the same box; B = x, unshifted.  5 pairs cover the 9 taps.
 //   MODE_POINTWISE (1x1 convolution, the late-fusion concat_convs): no halo, one tap:
 //                  A = 128 output channels of dy, B = NB blocks of 64 input channels of x.
+//   MODE_RS_SPLIT (Cout == 64 blocks, Cin % 64 == 0): the vertical tap offset is carried by dy and
+//                  the horizontal one by x, dW[(r,s)] = sum_q dy[q - (r-1, 0)] x[q + (0, s-1)]:
+//                  A = dy box with a vertical halo (16 x 6 px), two filter rows stacked on M (second
+//                  64-row block LBO = one box row further), B = x box with a horizontal halo
+//                  (18 x 4 px), the three taps s stacked on N (N = 192, blocks one pixel apart).
+//                  One MMA covers 6 taps: 2 MMAs and 20 KB of operand reads per K step where
+//                  MODE_DY_SHIFT needs 5 MMAs and 30 KB (it is shared-memory bound at 60 % tensor pipe).
 //   MODE_X_STACK  (Cout == 64 blocks with < 64 input channels, i.e. the first layer): with N = 16
 //                  an M128 MMA is 8 tensor cycles of work for 4.5 KB of operands, and MODE_DY_SHIFT
 //                  re-reads the dy operand for each of its 20 MMAs per stage (90 KB, shared-memory
@@ -61,12 +68,13 @@ struct WgradParams {
 template <int MODE, int NBW, int NB>
 struct WgCfg {
   // A = dy.  mode 0: two [64 px][64 co] blocks; mode 1: one haloed box 18 x 6 px (padded slot)
-  static constexpr int kABlock = MODE != 1 ? kWgBK * 128 : kWgBoxW * (kWgTH + 2) * 128;
+  static constexpr int kABlock = MODE == 4 ? kWgTW * (kWgTH + 2) * 128
+                               : (MODE != 1 ? kWgBK * 128 : kWgBoxW * (kWgTH + 2) * 128);
   static constexpr int kABytes = (MODE == 0 || MODE == 2) ? 2 * kABlock : kABlock;          // TMA bytes
   static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024 + (MODE != 1 ? 0 : 1024);
   // B = x.  mode 0: NB blocks of one filter row with halo [18 x 4 px][64 ci]; mode 1: [64 px][NBW];
   // mode 2: NB blocks [64 px][64 ci]
-  static constexpr int kBBlock = MODE == 0 ? kWgBoxW * kWgTH * 128
+  static constexpr int kBBlock = (MODE == 0 || MODE == 4) ? kWgBoxW * kWgTH * 128
                                : (MODE == 3 ? kWgBoxW * (kWgTH + 2) * NBW * 2 : kWgBK * NBW * 2);
   static constexpr int kBBytes = (MODE == 0 || MODE == 2) ? NB * kBBlock : kBBlock;
   static constexpr int kBSlot = (kBBytes + 1023) / 1024 * 1024;
@@ -74,8 +82,8 @@ struct WgCfg {
   static constexpr int kTxBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kGroups = (MODE == 0 || MODE == 3) ? 3 : (MODE == 1 ? 5 : 1);
-  static constexpr int kN = MODE == 3 ? 3 * NBW : NBW * NB;   // UMMA N per group
+  static constexpr int kGroups = (MODE == 0 || MODE == 3) ? 3 : (MODE == 1 ? 5 : (MODE == 4 ? 2 : 1));
+  static constexpr int kN = (MODE == 3 || MODE == 4) ? 3 * NBW : NBW * NB;   // UMMA N per group
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -93,7 +101,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   using Cfg = WgCfg<MODE, NBW, NB>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kIdesc = make_idesc_bf16(MODE == 3 ? 64 : 128, Cfg::kN, 1, 1);
-  constexpr uint32_t kBRow = (MODE == 0 || MODE == 2) ? 128 : NBW * 2;   // bytes per pixel row of B
+  constexpr uint32_t kBRow = (MODE == 0 || MODE == 2 || MODE == 4) ? 128 : NBW * 2;   // bytes per pixel row of B
   constexpr uint32_t kBSwz = kBRow;
   constexpr uint32_t kBSBO = 8 * kBRow;
 
@@ -119,7 +127,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   // second 64-channel block of A; a 64-channel pointwise layer re-reads the first block (its
   // duplicate accumulator rows are discarded)
   const int co1 = (MODE == 2 && co0 + 64 >= p.Cout) ? co0 : co0 + 64;
-  const int ci0 = ci_grp * (MODE == 3 ? NBW : Cfg::kN);
+  const int ci0 = ci_grp * ((MODE == 3 || MODE == 4) ? NBW : Cfg::kN);
   const int t_begin = (int)(((long)p.num_pix_tiles * split) / p.ksplit);
   const int t_end = (int)(((long)p.num_pix_tiles * (split + 1)) / p.ksplit);
 
@@ -171,6 +179,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         } else if (MODE == 3) {
           tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0, h0, img);
           tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0 - 1, h0 - 1, img);
+        } else if (MODE == 4) {
+          tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0, h0 - 1, img);
+          tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0 - 1, h0, img);
         } else {
           tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0 - 1, h0 - 1, img);
           tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0, h0, img);
@@ -208,6 +219,12 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
             } else if (MODE == 2) {
               a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
               b_lo = (b_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kBBlock) >> 4) << 16);
+            } else if (MODE == 4) {
+              // A: dy box row k + 1 - r with r = 1 (group 0) or r = 2 (group 1) in M rows 0..63 and
+              // the box row below it (r - 1) in M rows 64..127 (group 1: a discarded duplicate).
+              // B: x box row k, taps s = 0..2 as N blocks one pixel apart.
+              a_lo = (a_addr16 + ((((k + 1 - g) * kWgTW) * 128) >> 4)) | ((uint32_t(kWgTW * 128) >> 4) << 16);
+              b_lo = (b_addr16 + ((k * kWgBoxW * 128) >> 4)) | ((128u >> 4) << 16);
             } else if (MODE == 3) {
               // A: dy row k of the tile, one 64-channel block.  B: x row k + r of the haloed box
               // (r = g), the three taps s = 0..2 as N blocks one pixel row (kBRow bytes) apart
@@ -239,7 +256,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 #pragma unroll
     for (int g = 0; g < Cfg::kGroups; ++g) {
       int co, tap;
-      if (MODE == 3) {
+      if (MODE == 4) {
+        co = co0 + (row & 63);
+        // group 0: filter rows 1 (M rows 0..63) and 0 (rows 64..127); group 1: filter row 2 and a discard
+        tap = g == 0 ? (row < 64 ? 3 : 0) : (row < 64 ? 6 : -1);   // + s per column chunk below
+      } else if (MODE == 3) {
         // M = 64 accumulator: rows 16q .. 16q+15 live in lanes 0..15 of TMEM lane quadrant q
         co = co0 + quad * 16 + (lane & 15);
         tap = lane < 16 ? g * 3 : -1;   // + s per column chunk below
@@ -260,7 +281,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         uint32_t r[16];
         tmem_ld_32x16(tmem_base + (uint32_t(quad * 32) << 16) + g * Cfg::kN + c * 16, r);
         tmem_ld_wait();
-        if (MODE == 3) {
+        if (MODE == 3 || MODE == 4) {
           // column chunk c = tap s = (16 c) / NBW, channels (16 c) % NBW ..
           if (tap >= 0) {
             float* d3 = ws + ((size_t)co * p.taps + tap + (c * 16) / NBW) * p.Cin + ci0 + (c * 16) % NBW;
@@ -333,6 +354,11 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl, int ta
     pl->items_r = 3;
     pl->items_ci = Cin / (64 * pl->nb);
     pl->n_items = (Cout / 128) * pl->items_ci * 3;
+  } else if (Cin % 64 == 0 && getenv("FPB200_WGRAD_DYSHIFT") == nullptr) {
+    pl->mode = 4; pl->nb = 1; pl->nbw = 64;
+    pl->items_r = 1;
+    pl->items_ci = Cin / 64;
+    pl->n_items = (Cout / 64) * pl->items_ci;
   } else if (Cin % 64 != 0) {
     pl->mode = 3; pl->nb = 1;
     pl->nbw = (Cin % 32 == 0) ? 32 : 16;
@@ -414,6 +440,10 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
     rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgTW, kWgTH);
     if (rc != FPB200_OK) return rc;
     rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, pl.nbw, kWgBoxW, kWgTH + 2);
+  } else if (pl.mode == 4) {
+    rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgTW, kWgTH + 2);
+    if (rc != FPB200_OK) return rc;
+    rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, 64, kWgBoxW, kWgTH);
   } else {
     rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgBoxW, kWgTH + 2);
     if (rc != FPB200_OK) return rc;
@@ -429,6 +459,7 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
   p.ws = reinterpret_cast<float*>(workspace);
   if (pl.mode == 0 && pl.nb == 2) rc = launch_wgrad<0, 64, 2>(tmDY, tmX, p, stream);
   else if (pl.mode == 0) rc = launch_wgrad<0, 64, 1>(tmDY, tmX, p, stream);
+  else if (pl.mode == 4) rc = launch_wgrad<4, 64, 1>(tmDY, tmX, p, stream);
   else if (pl.mode == 3 && pl.nbw == 32) rc = launch_wgrad<3, 32, 1>(tmDY, tmX, p, stream);
   else if (pl.mode == 3) rc = launch_wgrad<3, 16, 1>(tmDY, tmX, p, stream);
   else if (pl.nbw == 64) rc = launch_wgrad<1, 64, 1>(tmDY, tmX, p, stream);

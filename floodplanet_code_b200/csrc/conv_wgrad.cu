@@ -19,29 +19,27 @@
 // the image): a tap is only a different descriptor start address, exactly as in the fprop
 // kernel, so each operand byte enters shared memory once per tile instead of once per tap.
 //
-// Two operand arrangements keep UMMA_M = 128 for every layer of the UNet:
-//   MODE_X_SHIFT  (Cout % 128 == 0): A = 128 output channels of dy (no halo); B = one filter
+// Operand arrangements (every layer of the UNet keeps the tensor cores on full-height M = 128 MMAs
+// except the first one, which is shared-memory bound either way):
+//   MODE_X_SHIFT  (0, Cout % 128 == 0): A = 128 output channels of dy (no halo); B = one filter
 //                  row of x, box 18 px wide, the three taps s = start address + s pixels.
 //                  Work item = (128 co, 64*NB ci, filter row r): 3 accumulators of 64*NB cols.
-//   MODE_DY_SHIFT (Cout == 64 blocks): the SHIFT moves to dy (dW[tap] = sum_q dy[q-tap] x[q]):
-//                  A = dy box with halo (18 x 6 px); two taps are stacked on M (2 x 64 co) by
-//                  pointing the descriptor's second 64-row block (LBO) at the other tap's
-//                  offset inside the same box; B = x, unshifted.  5 pairs cover the 9 taps.
-//   MODE_POINTWISE (1x1 convolution, the late-fusion concat_convs): no halo, one tap:
+//   MODE_POINTWISE (2, 1x1 convolution, the late-fusion concat_convs): no halo, one tap:
 //                  A = 128 output channels of dy, B = NB blocks of 64 input channels of x.
-//   MODE_RS_SPLIT (Cout == 64 blocks, Cin % 64 == 0): the vertical tap offset is carried by dy and
+//   MODE_RS_SPLIT (4, Cout == 64 blocks, Cin % 64 == 0): the vertical tap offset is carried by dy and
 //                  the horizontal one by x, dW[(r,s)] = sum_q dy[q - (r-1, 0)] x[q + (0, s-1)]:
 //                  A = dy box with a vertical halo (16 x 6 px), two filter rows stacked on M (second
 //                  64-row block LBO = one box row further), B = x box with a horizontal halo
 //                  (18 x 4 px), the three taps s stacked on N (N = 192, blocks one pixel apart).
-//                  One MMA covers 6 taps: 2 MMAs and 20 KB of operand reads per K step where
-//                  MODE_DY_SHIFT needs 5 MMAs and 30 KB (it is shared-memory bound at 60 % tensor pipe).
-//   MODE_X_STACK  (Cout == 64 blocks with < 64 input channels, i.e. the first layer): with N = 16
-//                  an M128 MMA is 8 tensor cycles of work for 4.5 KB of operands, and MODE_DY_SHIFT
-//                  re-reads the dy operand for each of its 20 MMAs per stage (90 KB, shared-memory
-//                  bound at 17 % tensor-pipe utilisation, ncu).  Here A = dy unshifted (M = 64),
-//                  B = x box with halo, and the three taps of a filter row are stacked on N
-//                  (N blocks one pixel apart, LBO = one pixel row): 12 MMAs and 42 KB per stage.
+//                  One MMA covers 6 taps: 2 MMAs and 20 KB of operand reads per K step.  (Its
+//                  predecessor shifted only dy and stacked tap PAIRS on M: 5 MMAs and 30 KB per K
+//                  step, shared-memory bound at 60 % tensor pipe; 64->64 @512^2 1.24 -> 1.15 ms.)
+//   MODE_X_STACK  (3, Cout == 64 blocks with < 64 input channels, i.e. the first layer): with N = 16
+//                  an M128 MMA is 8 tensor cycles of work for 4.5 KB of operands (the tap-pair
+//                  arrangement re-read the dy operand for each of its 20 MMAs per stage: 90 KB,
+//                  17 % tensor-pipe utilisation, ncu).  Here A = dy unshifted (M = 64), B = x box
+//                  with halo, and the three taps of a filter row are stacked on N (N blocks one
+//                  pixel apart, LBO = one pixel row): 12 MMAs and 42 KB per stage, 0.905 -> 0.652 ms.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -59,7 +57,7 @@ struct WgradParams {
   int ksplit;
   int n_items;      // output tiles
   int items_ci;     // number of ci groups (item = co_grp * items_ci * items_r + ci_grp * items_r + r)
-  int items_r;      // 3 in MODE_X_SHIFT, 1 in MODE_DY_SHIFT
+  int items_r;      // 3 in MODE_X_SHIFT, 1 otherwise
   int Cout, Cin;    // Cin = padded input channels (layout of the partials)
   int taps;         // 9 (3x3) or 1 (pointwise)
   float* ws;        // [ksplit][Cout][taps][Cin]
@@ -67,13 +65,12 @@ struct WgradParams {
 
 template <int MODE, int NBW, int NB>
 struct WgCfg {
-  // A = dy.  mode 0: two [64 px][64 co] blocks; mode 1: one haloed box 18 x 6 px (padded slot)
-  static constexpr int kABlock = MODE == 4 ? kWgTW * (kWgTH + 2) * 128
-                               : (MODE != 1 ? kWgBK * 128 : kWgBoxW * (kWgTH + 2) * 128);
+  // A = dy.  modes 0, 2: two [64 px][64 co] blocks; mode 3: one; mode 4: box 16 x 6 px (vertical halo)
+  static constexpr int kABlock = MODE == 4 ? kWgTW * (kWgTH + 2) * 128 : kWgBK * 128;
   static constexpr int kABytes = (MODE == 0 || MODE == 2) ? 2 * kABlock : kABlock;          // TMA bytes
-  static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024 + (MODE != 1 ? 0 : 1024);
-  // B = x.  mode 0: NB blocks of one filter row with halo [18 x 4 px][64 ci]; mode 1: [64 px][NBW];
-  // mode 2: NB blocks [64 px][64 ci]
+  static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;
+  // B = x.  modes 0, 4: (NB blocks of) one filter row with a horizontal halo [18 x 4 px][64 ci];
+  // mode 2: NB blocks [64 px][64 ci]; mode 3: haloed box [18 x 6 px][NBW ci]
   static constexpr int kBBlock = (MODE == 0 || MODE == 4) ? kWgBoxW * kWgTH * 128
                                : (MODE == 3 ? kWgBoxW * (kWgTH + 2) * NBW * 2 : kWgBK * NBW * 2);
   static constexpr int kBBytes = (MODE == 0 || MODE == 2) ? NB * kBBlock : kBBlock;
@@ -82,22 +79,16 @@ struct WgCfg {
   static constexpr int kTxBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kGroups = (MODE == 0 || MODE == 3) ? 3 : (MODE == 1 ? 5 : (MODE == 4 ? 2 : 1));
+  static constexpr int kGroups = (MODE == 0 || MODE == 3) ? 3 : (MODE == 4 ? 2 : 1);
   static constexpr int kN = (MODE == 3 || MODE == 4) ? 3 * NBW : NBW * NB;   // UMMA N per group
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
-
-// MODE_DY_SHIFT tap pairing.  Box row offset of tap (r,s) is (2-r)*18 + (2-s); group g stacks
-// tap 8-2g (M rows 0..63) and tap 7-2g (M rows 64..127); group 4 is tap 0 plus a discarded half.
-__host__ __device__ constexpr int wg_pair_offset(int g) {
-  return g == 0 ? 0 : (g == 1 ? 2 : (g == 2 ? kWgBoxW + 1 : (g == 3 ? 2 * kWgBoxW : 2 * kWgBoxW + 2)));
-}
-__host__ __device__ constexpr int wg_pair_lbo_rows(int g) { return g == 1 ? kWgBoxW - 2 : 1; }
 
 template <int MODE, int NBW, int NB>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                      const WgradParams p) {
+  static_assert(MODE == 0 || MODE == 2 || MODE == 3 || MODE == 4, "unknown wgrad mode");
   using Cfg = WgCfg<MODE, NBW, NB>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kIdesc = make_idesc_bf16(MODE == 3 ? 64 : 128, Cfg::kN, 1, 1);
@@ -179,12 +170,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         } else if (MODE == 3) {
           tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0, h0, img);
           tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0 - 1, h0 - 1, img);
-        } else if (MODE == 4) {
+        } else {
           tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0, h0 - 1, img);
           tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0 - 1, h0, img);
-        } else {
-          tma_load_4d(sa, &tmDY, full_bar(stage), co0, w0 - 1, h0 - 1, img);
-          tma_load_4d(sb, &tmX, full_bar(stage), ci0, w0, h0, img);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
@@ -225,16 +213,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
               // B: x box row k, taps s = 0..2 as N blocks one pixel apart.
               a_lo = (a_addr16 + ((((k + 1 - g) * kWgTW) * 128) >> 4)) | ((uint32_t(kWgTW * 128) >> 4) << 16);
               b_lo = (b_addr16 + ((k * kWgBoxW * 128) >> 4)) | ((128u >> 4) << 16);
-            } else if (MODE == 3) {
-              // A: dy row k of the tile, one 64-channel block.  B: x row k + r of the haloed box
-              // (r = g), the three taps s = 0..2 as N blocks one pixel row (kBRow bytes) apart
+            } else {
+              // MODE 3.  A: dy row k of the tile, one 64-channel block.  B: x row k + r of the haloed
+              // box (r = g), the three taps s = 0..2 as N blocks one pixel row (kBRow bytes) apart
               a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
               b_lo = (b_addr16 + ((((k + g) * kWgBoxW) * kBRow) >> 4)) | ((kBRow >> 4) << 16);
-            } else {
-              // A: haloed dy box; first M block at the pair's first tap, second block LBO further
-              a_lo = (a_addr16 + (((k * kWgBoxW + wg_pair_offset(g)) * 128) >> 4)) |
-                     ((uint32_t(wg_pair_lbo_rows(g) * 128) >> 4) << 16);
-              b_lo = (b_addr16 + ((k * kWgTW * kBRow) >> 4)) | (1u << 16);
             }
             if (leader)
               umma_bf16(tmem_base + g * Cfg::kN, smem_desc_join(a_lo, kAHi),
@@ -267,35 +250,23 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
       } else if (MODE == 0) {
         co = co0 + row;
         tap = r_idx * 3 + g;
-      } else if (MODE == 2) {
+      } else {
         co = co0 + row;
         tap = co < p.Cout ? 0 : -1;
         if (tap < 0) co = 0;
-      } else {
-        co = co0 + (row & 63);
-        tap = (row < 64) ? 8 - 2 * g : 7 - 2 * g;   // group 4: tap 0 and a discarded half (-1)
       }
-      float* dst = ws + ((size_t)co * p.taps + (tap < 0 ? 0 : tap)) * p.Cin + ci0;
 #pragma unroll
       for (int c = 0; c < Cfg::kN / 16; ++c) {
         uint32_t r[16];
         tmem_ld_32x16(tmem_base + (uint32_t(quad * 32) << 16) + g * Cfg::kN + c * 16, r);
         tmem_ld_wait();
-        if (MODE == 3 || MODE == 4) {
-          // column chunk c = tap s = (16 c) / NBW, channels (16 c) % NBW ..
-          if (tap >= 0) {
-            float* d3 = ws + ((size_t)co * p.taps + tap + (c * 16) / NBW) * p.Cin + ci0 + (c * 16) % NBW;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 o;
-              o.x = have ? __uint_as_float(r[q * 4 + 0]) : 0.f;
-              o.y = have ? __uint_as_float(r[q * 4 + 1]) : 0.f;
-              o.z = have ? __uint_as_float(r[q * 4 + 2]) : 0.f;
-              o.w = have ? __uint_as_float(r[q * 4 + 3]) : 0.f;
-              *reinterpret_cast<float4*>(d3 + q * 4) = o;
-            }
-          }
-        } else if (tap >= 0) {
+        if (tap >= 0) {
+          // modes 3 / 4: the accumulator columns are [tap s][NBW channels]; column chunk c belongs to
+          // tap s = 16c / NBW, channels 16c % NBW ..; modes 0 / 2: one tap per group, kN channels
+          constexpr bool kTapsOnN = MODE == 3 || MODE == 4;
+          const int tap_c = kTapsOnN ? tap + (c * 16) / NBW : tap;
+          const int ch_c = kTapsOnN ? (c * 16) % NBW : c * 16;
+          float* dst = ws + ((size_t)co * p.taps + tap_c) * p.Cin + ci0 + ch_c;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float4 o;
@@ -303,7 +274,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
             o.y = have ? __uint_as_float(r[q * 4 + 1]) : 0.f;
             o.z = have ? __uint_as_float(r[q * 4 + 2]) : 0.f;
             o.w = have ? __uint_as_float(r[q * 4 + 3]) : 0.f;
-            *reinterpret_cast<float4*>(dst + c * 16 + q * 4) = o;
+            *reinterpret_cast<float4*>(dst + q * 4) = o;
           }
         }
       }
@@ -354,20 +325,14 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl, int ta
     pl->items_r = 3;
     pl->items_ci = Cin / (64 * pl->nb);
     pl->n_items = (Cout / 128) * pl->items_ci * 3;
-  } else if (Cin % 64 == 0 && getenv("FPB200_WGRAD_DYSHIFT") == nullptr) {
+  } else if (Cin % 64 == 0) {
     pl->mode = 4; pl->nb = 1; pl->nbw = 64;
     pl->items_r = 1;
     pl->items_ci = Cin / 64;
     pl->n_items = (Cout / 64) * pl->items_ci;
-  } else if (Cin % 64 != 0) {
+  } else {
     pl->mode = 3; pl->nb = 1;
     pl->nbw = (Cin % 32 == 0) ? 32 : 16;
-    pl->items_r = 1;
-    pl->items_ci = Cin / pl->nbw;
-    pl->n_items = (Cout / 64) * pl->items_ci;
-  } else {
-    pl->mode = 1; pl->nb = 1;
-    pl->nbw = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
     pl->items_r = 1;
     pl->items_ci = Cin / pl->nbw;
     pl->n_items = (Cout / 64) * pl->items_ci;
@@ -440,14 +405,10 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
     rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgTW, kWgTH);
     if (rc != FPB200_OK) return rc;
     rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, pl.nbw, kWgBoxW, kWgTH + 2);
-  } else if (pl.mode == 4) {
+  } else {
     rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgTW, kWgTH + 2);
     if (rc != FPB200_OK) return rc;
     rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, 64, kWgBoxW, kWgTH);
-  } else {
-    rc = make_tmap_act(&tmDY, dy, N, H, W, Cout, lddy, 64, kWgBoxW, kWgTH + 2);
-    if (rc != FPB200_OK) return rc;
-    rc = make_tmap_act(&tmX, x, N, H, W, Cin, ldx, pl.nbw, kWgTW, kWgTH);
   }
   if (rc != FPB200_OK) return rc;
   WgradParams p;
@@ -461,10 +422,7 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
   else if (pl.mode == 0) rc = launch_wgrad<0, 64, 1>(tmDY, tmX, p, stream);
   else if (pl.mode == 4) rc = launch_wgrad<4, 64, 1>(tmDY, tmX, p, stream);
   else if (pl.mode == 3 && pl.nbw == 32) rc = launch_wgrad<3, 32, 1>(tmDY, tmX, p, stream);
-  else if (pl.mode == 3) rc = launch_wgrad<3, 16, 1>(tmDY, tmX, p, stream);
-  else if (pl.nbw == 64) rc = launch_wgrad<1, 64, 1>(tmDY, tmX, p, stream);
-  else if (pl.nbw == 32) rc = launch_wgrad<1, 32, 1>(tmDY, tmX, p, stream);
-  else rc = launch_wgrad<1, 16, 1>(tmDY, tmX, p, stream);
+  else rc = launch_wgrad<3, 16, 1>(tmDY, tmX, p, stream);
   if (rc != FPB200_OK) return rc;
   const long total = (long)Cout * 9 * Cin;
   long g = (total + 255) / 256;

@@ -9,7 +9,16 @@ per = collections.defaultdict(lambda: collections.defaultdict(float)); cnt = col
 def short(k):
     k = re.sub(r'\(.*$', '', k).replace('fp::', '').replace('void ', '')
     return k[:70]
+lo, hi = -1, 1 << 60
+if '--step' in sys.argv:      # trim to one training step: first ingest_kernel .. next repack_batch_kernel
+    ids = {}
+    for r in rows[1:]: ids.setdefault(int(r[iID]), r[iK])
+    starts = [i for i in sorted(ids) if 'ingest_kernel' in ids[i]]
+    lo = starts[0]
+    ends = [i for i in sorted(ids) if 'repack_batch_kernel' in ids[i] and i > lo]
+    hi = ends[0] if ends else max(ids)
 for r in rows[1:]:
+    if not (lo <= int(r[iID]) <= hi): continue
     k = short(r[iK]); v = float(r[iV].replace(',', '')); u = r[iU]
     if r[iM] == 'gpu__time_duration.sum':
         v = v / 1e6 if u in ('ns', 'nsecond') else (v / 1e3 if u in ('us', 'usecond') else v)   # -> ms

@@ -22,8 +22,11 @@
 // Operand arrangements (every layer of the UNet keeps the tensor cores on full-height M = 128 MMAs
 // except the first one, which is shared-memory bound either way):
 //   MODE_X_SHIFT  (0, Cout % 128 == 0): A = 128 output channels of dy (no halo); B = one filter
-//                  row of x, box 18 px wide, the three taps s = start address + s pixels.
-//                  Work item = (128 co, 64*NB ci, filter row r): 3 accumulators of 64*NB cols.
+//                  row of x, box 18 px wide, the three taps s stacked on N (N = 192 per 64-channel
+//                  block of x, the N blocks one pixel apart), so dy is read once per K step and
+//                  channel block instead of once per tap (24 -> 20 KB of operand reads per K step
+//                  at NB = 2, which sat exactly on the 128 B/clk shared-memory limit: +3 %).
+//                  Work item = (128 co, 64*NB ci, filter row r): NB accumulators of 192 cols.
 //   MODE_POINTWISE (2, 1x1 convolution, the late-fusion concat_convs): no halo, one tap:
 //                  A = 128 output channels of dy, B = NB blocks of 64 input channels of x.
 //   MODE_RS_SPLIT (4, Cout == 64 blocks, Cin % 64 == 0): the vertical tap offset is carried by dy and
@@ -79,8 +82,9 @@ struct WgCfg {
   static constexpr int kTxBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kGroups = (MODE == 0 || MODE == 3) ? 3 : (MODE == 4 ? 2 : 1);
-  static constexpr int kN = (MODE == 3 || MODE == 4) ? 3 * NBW : NBW * NB;   // UMMA N per group
+  // mode 0: one group per 64-channel block of x, the three taps of the filter row stacked on N
+  static constexpr int kGroups = MODE == 0 ? NB : (MODE == 3 ? 3 : (MODE == 4 ? 2 : 1));
+  static constexpr int kN = (MODE == 0 || MODE == 3 || MODE == 4) ? 3 * NBW : NBW * NB;   // UMMA N per group
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -118,7 +122,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   // second 64-channel block of A; a 64-channel pointwise layer re-reads the first block (its
   // duplicate accumulator rows are discarded)
   const int co1 = (MODE == 2 && co0 + 64 >= p.Cout) ? co0 : co0 + 64;
-  const int ci0 = ci_grp * ((MODE == 3 || MODE == 4) ? NBW : Cfg::kN);
+  const int ci0 = ci_grp * ((MODE == 3 || MODE == 4) ? NBW : NBW * NB);
   const int t_begin = (int)(((long)p.num_pix_tiles * split) / p.ksplit);
   const int t_end = (int)(((long)p.num_pix_tiles * (split + 1)) / p.ksplit);
 
@@ -201,9 +205,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
             if (MODE == 0) {
               // A: dy rows k*16.. of both 64-co blocks (LBO = block pitch)
               a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
-              // B: x row k of the haloed filter-row box, shifted by tap s = g pixels
-              b_lo = (b_addr16 + (((k * kWgBoxW + g) * 128) >> 4)) |
-                     ((uint32_t(Cfg::kBBlock) >> 4) << 16);
+              // B: x row k of the haloed filter-row box of channel block g, the taps s = 0..2 as N
+              // blocks one pixel apart (dy is read once per K step and channel block, not once per tap)
+              b_lo = (b_addr16 + ((g * Cfg::kBBlock + k * kWgBoxW * 128) >> 4)) | ((128u >> 4) << 16);
             } else if (MODE == 2) {
               a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
               b_lo = (b_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kBBlock) >> 4) << 16);
@@ -249,7 +253,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         tap = lane < 16 ? g * 3 : -1;   // + s per column chunk below
       } else if (MODE == 0) {
         co = co0 + row;
-        tap = r_idx * 3 + g;
+        tap = r_idx * 3;          // + s per column chunk below; group g = 64-channel block g
       } else {
         co = co0 + row;
         tap = co < p.Cout ? 0 : -1;
@@ -263,9 +267,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         if (tap >= 0) {
           // modes 3 / 4: the accumulator columns are [tap s][NBW channels]; column chunk c belongs to
           // tap s = 16c / NBW, channels 16c % NBW ..; modes 0 / 2: one tap per group, kN channels
-          constexpr bool kTapsOnN = MODE == 3 || MODE == 4;
+          constexpr bool kTapsOnN = MODE == 0 || MODE == 3 || MODE == 4;
           const int tap_c = kTapsOnN ? tap + (c * 16) / NBW : tap;
-          const int ch_c = kTapsOnN ? (c * 16) % NBW : c * 16;
+          const int ch_c = kTapsOnN ? (c * 16) % NBW + (MODE == 0 ? g * NBW : 0) : c * 16;
           float* dst = ws + ((size_t)co * p.taps + tap_c) * p.Cin + ci0 + ch_c;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

@@ -456,12 +456,13 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        const CUtensorMap& tmYL, const HaloParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, KCH, TAPS, EW>;
   auto kern = conv3x3_halo_kernel<BN, KCH, TAPS, EW>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};   // cudaFuncSetAttribute is per device
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
         cudaSuccess)
       return check_launch("conv3x3_halo smem attribute");
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   const int items = p.num_patches * p.num_n_blks;
   int grid = sm_count();

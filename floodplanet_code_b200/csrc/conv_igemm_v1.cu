@@ -294,12 +294,13 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
                        cudaStream_t stream) {
   using Cfg = ConvCfg<BN, KCH>;
   auto kern = conv3x3_igemm_kernel<BN, KCH>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};   // cudaFuncSetAttribute is per device
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
         cudaSuccess)
       return check_launch("conv3x3 smem attribute");
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_blks;
   int grid = sm_count();

@@ -365,12 +365,13 @@ static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const W
                         cudaStream_t stream) {
   using Cfg = WgCfg<MODE, NBW, NB>;
   auto kern = conv3x3_wgrad_kernel<MODE, NBW, NB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};   // cudaFuncSetAttribute is per device
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
         cudaSuccess)
       return check_launch("wgrad smem attribute");
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   kern<<<p.n_items * p.ksplit, kWgThreads, Cfg::kSmemBytes, stream>>>(tmDY, tmX, p);
   return check_launch("conv3x3_wgrad");

@@ -1141,12 +1141,13 @@ int fpb200_upsample2x_pad_concat_bwd(const void* dout, long lddo, void* dx, long
   const int chunk_cols = up_bwd_chunk_cols(C);
   const int chunks = (w + chunk_cols - 1) / chunk_cols;
   const int smem = (2 * chunk_cols + kUpBwdHalo) * C * (int)sizeof(float);
-  static int smem_set = 0;
-  if (smem > smem_set) {
+  static int smem_set[kMaxDevices] = {0};   // per device, like the attribute itself
+  const int dev_ = current_device();
+  if (smem > smem_set[dev_]) {
     if (cudaFuncSetAttribute(upsample2x_pad_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              64 * 1024) != cudaSuccess)
       return check_launch("upsample2x_pad_concat_bwd smem attribute");
-    smem_set = 64 * 1024;
+    smem_set[dev_] = 64 * 1024;
   }
   // 32-bit element offsets inside one image of dout
   if (smem > 64 * 1024 || (long)Ho * Wo * lddo >= (1L << 31)) return FPB200_ERR_SHAPE;

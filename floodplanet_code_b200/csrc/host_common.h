@@ -13,14 +13,23 @@
 
 namespace fp {
 
+// Per-device caches: one process may drive several devices (a model on cuda:1 while cuda:0 is
+// current elsewhere), so nothing device-dependent is kept in a single process-wide static.
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 inline int check_launch(const char* what) {

@@ -99,14 +99,30 @@ def param_names(n_channels: int) -> List[str]:
     return conv_param_names(unet_conv_specs(n_channels)) + ["outc.conv.weight", "outc.conv.bias"]
 
 
+class _RawWriteEpochs:
+    """Process-wide counters for writes torch's version counters cannot see: kernels that update
+    parameters through raw pointers (fused Adam, CUDA-graph replays of it), `.data` writes
+    (`dist.broadcast(p.data)`) and training-mode BatchNorm kernels rewriting the running
+    statistics.  Every engine of every module keys its caches (packed bf16 weight copies, folded
+    eval-mode BatchNorm coefficients) on them, so one bump invalidates the `_engine`,
+    `_enc_engine` and `_dec_engine` views of the same parameters alike."""
+    param = 0
+    bn = 0
+
+
+def note_raw_parameter_write() -> None:
+    """Call after parameters / buffers were modified behind torch's back (see _RawWriteEpochs)."""
+    _RawWriteEpochs.param += 1
+    _RawWriteEpochs.bn += 1
+
+
 class PackedWeights:
     """bf16 GEMM-operand copies of the fp32 OIHW master weights, refreshed when a parameter's
-    version counter moves (optimizer step, load_state_dict)."""
+    version counter moves (optimizer step, load_state_dict) or a raw write was announced."""
 
     def __init__(self):
         self._fprop: Dict[str, Tuple[int, torch.Tensor]] = {}
         self._dgrad: Dict[str, Tuple[int, torch.Tensor]] = {}
-        self.generation = 0
         # when True every lookup re-packs into the SAME buffer (CUDA-graph capture: the replayed
         # graph must contain the repack kernels because the optimiser changes the masters)
         self.always_repack = False
@@ -135,10 +151,14 @@ class PackedWeights:
 
     def invalidate(self) -> None:
         """For updates torch cannot see (raw-pointer kernels such as the fused Adam)."""
-        self.generation += 1
+        note_raw_parameter_write()
+
+    @property
+    def generation(self) -> int:
+        return _RawWriteEpochs.param
 
     def _key(self, w: torch.Tensor):
-        return (w._version, w.data_ptr(), w.device, self.generation)
+        return (w._version, w.data_ptr(), w.device, _RawWriteEpochs.param)
 
     def _lookup(self, table, name: str, w: torch.Tensor, pack):
         key = self._key(w)
@@ -252,7 +272,6 @@ class _Schedule:
         self.overlap_wgrad = False
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._fold_cache: Dict[str, Tuple[tuple, torch.Tensor, torch.Tensor]] = {}
-        self._bn_gen = 0
         self.launches = 0  # kernels launched by the last forward/backward (for bench accounting)
         self.names: List[str] = []
 
@@ -311,7 +330,7 @@ class _Schedule:
         shift = torch.empty(s.cout, **fw.f32)
         a = out_view if out_view is not None else torch.empty((n, hh, ww, s.cout), **fw.bf)
         if fw.training:
-            self._bn_gen += 1          # running statistics are about to be rewritten by a kernel
+            _RawWriteEpochs.bn += 1    # running statistics are about to be rewritten by a kernel
             y = torch.empty((n, hh, ww, s.cout), **fw.bf)
             parts = torch.empty((fw.stat_rows, 2, s.cout), **fw.f32)
             self._timed("fprop", s, n, hh * ww,
@@ -338,11 +357,12 @@ class _Schedule:
                 return y, scale, shift
         else:
             # folded eval-mode coefficients are cached per layer until a parameter / running statistic
-            # can have changed: tensor version counters, plus the two generation counters that cover
-            # raw-pointer writers (fused Adam -> packed.generation, training-mode BatchNorm -> _bn_gen)
+            # can have changed: tensor version counters, plus the two process-wide epochs that cover
+            # raw-pointer writers (fused Adam / graph replay / broadcast -> param, training-mode
+            # BatchNorm of ANY engine -> bn)
             rm, rv = buffers[f"{s.bn}.running_mean"], buffers[f"{s.bn}.running_var"]
             key = tuple((t._version, t.data_ptr()) for t in (gamma, beta, bias, rm, rv)) + (
-                self.packed.generation, self._bn_gen)
+                _RawWriteEpochs.param, _RawWriteEpochs.bn)
             hit = self._fold_cache.get(s.bn)
             if hit is not None and hit[0] == key:
                 scale, shift = hit[1], hit[2]

@@ -12,6 +12,7 @@ from typing import Dict
 
 import torch
 
+from .engine import note_raw_parameter_write
 from .optim import FusedAdam
 
 
@@ -61,4 +62,9 @@ class GraphedTrainStep:
 
     def replay(self) -> torch.Tensor:
         self.graph.replay()
+        # the replay updated the master weights, BatchNorm affine parameters and running statistics
+        # through raw pointers: no tensor version moved, so announce it (host-only, free) -- otherwise
+        # an eval / validation forward after replays would reuse stale packed weights and folded
+        # BatchNorm coefficients
+        note_raw_parameter_write()
         return self.loss

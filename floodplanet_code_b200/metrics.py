@@ -6,8 +6,15 @@ come for free from the cross-entropy kernel (``MaskedCrossEntropyLoss.last_confu
 the per-step metric update costs no extra pass over the 16.8 M pixels.
 
 With targets equal to ``ignore_index`` removed, micro statistics over C classes are
-``tp = trace``, ``fp = fn = total - trace`` and therefore
-  Accuracy = F1 = tp / total,   Jaccard = tp / (tp + fp + fn) = tp / (2*total - tp).
+``tp = trace``, ``fp = fn = total - trace`` and therefore  Accuracy = F1 = tp / total.
+
+Jaccard follows torchmetrics >= 0.11 (the version the reference's ``task="multiclass"`` arguments and
+its ``val_MulticlassJaccardIndex`` checkpoint monitor, fit.py:80-85, imply; torchmetrics itself is a
+third-party dependency that is not vendored in the reference): per class ``denom_c = colsum_c +
+rowsum_c - diag_c``; micro = ``sum(diag) / (sum(denom) - denom[ignore_index])`` when
+``0 <= ignore_index < C``.  The ignored class has an empty target row, so ``denom[ignore_index]``
+is the number of valid pixels PREDICTED as the ignored class:
+  Jaccard = tp / (2*total - tp - colsum[ignore_index])      (= tp / (2*total - tp) without ignore_index).
 """
 from __future__ import annotations
 
@@ -57,7 +64,10 @@ class MicroSegmentationMetrics:
         tp = conf.diagonal().sum()
         total = conf.sum()
         acc = torch.nan_to_num(tp / total).to(torch.float32)
-        jac = torch.nan_to_num(tp / (2 * total - tp)).to(torch.float32)
+        denom = 2 * total - tp
+        if self.ignore_index is not None and 0 <= self.ignore_index < conf.shape[0]:
+            denom = denom - conf[:, self.ignore_index].sum()
+        jac = torch.nan_to_num(tp / denom).to(torch.float32)
         p = self.prefix
         return {f"{p}MulticlassF1Score": acc, f"{p}MulticlassJaccardIndex": jac,
                 f"{p}MulticlassAccuracy": acc.clone()}

@@ -9,6 +9,7 @@ buffer).
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -510,3 +511,38 @@ def plane_mean_std(image: torch.Tensor):
                                           _stream())
     capi.check(st, "plane_mean_std_f32", planes=n * c, hw=h * w)
     return mean, std
+
+
+# ------------------------------------------------------------------------------------------
+# Device guard: every launcher runs on the device (and that device's current stream) of its
+# tensors, not on whatever device happens to be current -- a model on cuda:1 while cuda:0 is the
+# current device must not launch on cuda:0's stream.  Same-device calls pay two attribute reads.
+def _first_cuda_device(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (list, tuple)):
+            for b in a:
+                if isinstance(b, torch.Tensor) and b.is_cuda:
+                    return b.device
+    return None
+
+
+def _device_guarded(fn):
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _first_cuda_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name, _fn in list(globals().items()):
+    if (callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_")
+            and _name not in ("nhwc_view", "stat_rows", "bn_bwd_rows", "head_bwd_rows", "ce_rows",
+                              "wgrad_workspace_bytes", "conv1x1_wgrad_workspace_bytes")):
+        globals()[_name] = _device_guarded(_fn)
+del _name, _fn

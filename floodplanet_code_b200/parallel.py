@@ -16,6 +16,7 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
+from .engine import note_raw_parameter_write
 from .unet import UNet
 
 
@@ -100,3 +101,6 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
     with torch.no_grad():
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t.data, src=src, group=group)
+    # writes through .data do not move Parameter._version: announce them so that packed bf16 weight
+    # copies and folded eval-mode BatchNorm coefficients made by an earlier forward are rebuilt
+    note_raw_parameter_write()

@@ -138,12 +138,21 @@ class UNet(nn.Module):
                     f"{t.device.type} tensor and there is no CPU fallback")
             if t.dim() != 4:
                 raise RuntimeError(f"expected NCHW input, got shape {tuple(t.shape)}")
+            if t.requires_grad and torch.is_grad_enabled():
+                raise RuntimeError(
+                    "floodplanet_b200.UNet does not produce gradients with respect to its input images "
+                    "(the first convolution has no dgrad on this path; the reference's training / "
+                    "inference scripts never ask for one) -- detach the input")
         engine = self._engine
         params = dict(self.named_parameters())
         needs_grad = (torch.is_grad_enabled() and self.training
                       and any(p.requires_grad for p in params.values()))
         if needs_grad:
             return _UNetFunction.apply(self, len(images), *images, *[params[n] for n in engine.names])
+        # eval mode (or no_grad): forward only.  Backward through running-statistics BatchNorm is not
+        # built (no caller in the reference differentiates an eval-mode forward: validation / infer /
+        # predict all run under no_grad); the logits carry no graph, so a `.backward()` on them fails
+        # loudly in torch rather than training nothing.  See INTEGRATION.md "Limits".
         with torch.no_grad():
             logits, _ = engine.forward(images, params, dict(self.named_buffers()),
                                        training=self.training, save=False)

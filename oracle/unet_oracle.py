@@ -320,13 +320,26 @@ def confusion_counts(pred: torch.Tensor, target: torch.Tensor, n_classes: int,
     return torch.bincount(idx, minlength=n_classes * n_classes).view(n_classes, n_classes)
 
 
-def micro_metrics(conf: torch.Tensor) -> Dict[str, float]:
+def micro_metrics(conf: torch.Tensor, ignore_index: Optional[int] = None) -> Dict[str, float]:
     """torchmetrics multiclass micro F1 / Jaccard / Accuracy with ignore_index
-    (water_seg_model.py:46-63) expressed on confusion counts."""
+    (water_seg_model.py:46-63) expressed on confusion counts (rows = target, ignored targets
+    already removed).  torchmetrics (>= 0.11, implied by the reference's ``task="multiclass"``
+    arguments; not vendored in /root/reference, not installed here) is restated from its published
+    algorithm: micro F1 = Accuracy = tp / (tp + fn); Jaccard per class denom_c = colsum_c + rowsum_c -
+    diag_c, micro = sum(diag) / (sum(denom) - denom[ignore_index]) when 0 <= ignore_index < C
+    (functional/classification/jaccard.py, `_jaccard_index_reduce`).  Written out per class here on
+    purpose, unlike the closed form the product uses.  PARITY UNPINNED for this one function: no
+    torchmetrics build is available to generate a fixture."""
     conf = conf.double()
-    tp, total = conf.diagonal().sum(), conf.sum()
-    acc = float(torch.nan_to_num(tp / total))
-    return {"F1": acc, "Accuracy": acc, "Jaccard": float(torch.nan_to_num(tp / (2 * total - tp)))}
+    c = conf.shape[0]
+    diag = conf.diagonal()
+    total = conf.sum()
+    acc = float(torch.nan_to_num(diag.sum() / total))
+    denom = conf.sum(0) + conf.sum(1) - diag
+    dsum = denom.sum()
+    if ignore_index is not None and 0 <= ignore_index < c:
+        dsum = dsum - denom[ignore_index]
+    return {"F1": acc, "Accuracy": acc, "Jaccard": float(torch.nan_to_num(diag.sum() / dsum))}
 
 
 def synthetic_batch(n: int, c: int, h: int, w: int, seed: int = 0, ignore_frac: float = 0.58,

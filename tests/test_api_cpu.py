@@ -117,10 +117,17 @@ def test_metrics_micro():
     pred = torch.tensor([1, 1, 2, 0, 1, 2])
     tgt = torch.tensor([1, 0, 1, 1, 1, 0])
     out = m(pred, tgt)
-    ref = O.micro_metrics(O.confusion_counts(pred, tgt, 3, 0))
+    ref = O.micro_metrics(O.confusion_counts(pred, tgt, 3, 0), ignore_index=0)
     assert float(out["train_MulticlassAccuracy"]) == pytest.approx(ref["Accuracy"])
     assert float(out["train_MulticlassJaccardIndex"]) == pytest.approx(ref["Jaccard"])
     assert float(m.compute()["train_MulticlassF1Score"]) == pytest.approx(ref["F1"])
+    # one valid pixel is predicted as the ignored class 0: tp 2, total 4 -> 2 / (8 - 2 - 1)
+    assert float(out["train_MulticlassJaccardIndex"]) == pytest.approx(2 / 5)
+    # ignore_index outside [0, C) (e.g. None / -100): plain tp / (2 total - tp)
+    m2 = MicroSegmentationMetrics(3, ignore_index=None)
+    o2 = m2(pred, tgt)
+    r2 = O.micro_metrics(O.confusion_counts(pred, tgt, 3, None), None)
+    assert float(o2["MulticlassJaccardIndex"]) == pytest.approx(r2["Jaccard"])
 
 
 def test_late_fusion_module_tree_equals_reference():

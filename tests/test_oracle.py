@@ -97,6 +97,12 @@ def test_micro_metrics_formulas():
     m = O.micro_metrics(conf)
     assert m["Accuracy"] == pytest.approx(0.5) and m["F1"] == pytest.approx(0.5)
     assert m["Jaccard"] == pytest.approx(5 / 15)
+    # torchmetrics >= 0.11 micro Jaccard with ignore_index inside [0, C): valid pixels PREDICTED as the
+    # ignored class leave the denominator (hand-worked: tp 5, total 10, 3 predicted as class 0)
+    m0 = O.micro_metrics(conf, ignore_index=0)
+    assert m0["Jaccard"] == pytest.approx(5 / (2 * 10 - 5 - 3))
+    assert m0["Accuracy"] == pytest.approx(0.5)
+    assert O.micro_metrics(conf, ignore_index=-100)["Jaccard"] == pytest.approx(5 / 15)
 
 
 def test_late_fusion_oracle_matches_reference_golden():

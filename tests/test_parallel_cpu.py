@@ -24,9 +24,14 @@ def _worker(rank, world, port, q):
     from floodplanet_code_b200.unet import UNet
     r, w, _ = init_distributed("gloo")
     assert (r, w) == (rank, world)
+    from floodplanet_code_b200 import engine as E
     torch.manual_seed(rank)            # different init per rank ...
     net = UNet(4, 3)
+    epoch0 = E._RawWriteEpochs.param
     broadcast_parameters(net)          # ... identical after the broadcast
+    # the broadcast writes through .data (no version counter moves), so it must announce itself:
+    # caches made by a forward BEFORE the broadcast would otherwise survive it
+    assert E._RawWriteEpochs.param > epoch0 and net._engine.packed.generation == E._RawWriteEpochs.param
     chk = torch.stack([p.detach().double().sum() for p in net.parameters()]).sum()
     gathered = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(gathered, chk)

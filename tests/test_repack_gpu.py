@@ -78,3 +78,102 @@ def test_eval_fold_cache_tracks_training_updates():
     fresh = UNet(4, 3)
     fresh.load_state_dict({k: v.detach().cpu() for k, v in model.model.state_dict().items()}, strict=True)
     assert torch.equal(e1, eval_logits(fresh.cuda()))
+
+
+def test_graph_replay_invalidates_eval_caches():
+    """a CUDA-graph replay updates masters, BatchNorm affine parameters and running
+    statistics through raw pointers; an eval forward after replays must see them (packed weights
+    and the folded BatchNorm coefficients are rebuilt), also after MORE replays."""
+    from floodplanet_code_b200.graph import GraphedTrainStep
+    from floodplanet_code_b200.optim import FusedAdam
+    from floodplanet_code_b200.unet import UNet
+    from floodplanet_code_b200.water_seg_model import WaterSegmentationModel
+    from oracle import unet_oracle as O
+    model = WaterSegmentationModel({"ms_image": 4}, 3, 1e-2, ignore_index=0)
+    model.model.load_state_dict(O.init_state_dict(4, 3, seed=0), strict=True)
+    model = model.cuda()
+    opt = FusedAdam(model.model, lr=1e-2)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 64, seed=1, block=8).items()}
+
+    def eval_logits(m):
+        m.eval()
+        with torch.no_grad():
+            return m(batch["image"]).clone()
+
+    def fresh_eval():
+        fresh = UNet(4, 3)
+        fresh.load_state_dict({k: v.detach().cpu() for k, v in model.model.state_dict().items()}, strict=True)
+        return eval_logits(fresh.cuda())
+
+    step = GraphedTrainStep(model, opt, batch, warmup_steps=3)
+    e_first = eval_logits(model.model)            # fills the fold cache and the packed-weight tables
+    assert torch.equal(e_first, fresh_eval())
+    for _ in range(2):
+        step.replay()
+    e1 = eval_logits(model.model)
+    assert not torch.equal(e1, e_first)
+    assert torch.equal(e1, fresh_eval())
+    for _ in range(2):
+        step.replay()
+    e2 = eval_logits(model.model)
+    assert not torch.equal(e2, e1)
+    assert torch.equal(e2, fresh_eval())
+
+
+def test_raw_data_writes_and_fused_adam_reach_every_engine():
+    """`p.data` writes (what broadcast_parameters does) announced with
+    note_raw_parameter_write(), and FusedAdam steps, must invalidate the caches of ALL engines over
+    the same parameters -- UNet.forward, UNet.encode and UNet.decode own separate engines."""
+    from floodplanet_code_b200.engine import note_raw_parameter_write
+    from floodplanet_code_b200.optim import FusedAdam
+    from floodplanet_code_b200.unet import UNet
+    from oracle import unet_oracle as O
+    from floodplanet_code_b200.loss import MaskedCrossEntropyLoss
+    net = UNet(4, 3)
+    net.load_state_dict(O.init_state_dict(4, 3, seed=0), strict=True)
+    net = net.cuda()
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 64, seed=1, block=8).items()}
+
+    def all_paths(m):
+        m.eval()
+        with torch.no_grad():
+            full = m(batch["image"]).clone()
+            feats = [f.clone() for f in m.encode(batch["image"])]
+            dec = m.decode(feats).clone()
+        return full, feats, dec
+
+    def fresh_paths():
+        fresh = UNet(4, 3)
+        fresh.load_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()}, strict=True)
+        return all_paths(fresh.cuda())
+
+    def same(a, b):
+        return torch.equal(a[0], b[0]) and all(torch.equal(x, y) for x, y in zip(a[1], b[1])) and torch.equal(a[2], b[2])
+
+    first = all_paths(net)                          # every engine now holds caches
+    assert same(first, fresh_paths())
+    other = O.init_state_dict(4, 3, seed=5)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            p.data.copy_(other[k].cuda())           # no version counter moves
+    note_raw_parameter_write()
+    second = all_paths(net)
+    assert not torch.equal(second[0], first[0])
+    assert same(second, fresh_paths())
+    # fused Adam through the main engine; the encode / decode engines must follow
+    opt = FusedAdam(net, lr=1e-2)
+    net.train()
+    loss = MaskedCrossEntropyLoss(0)(net(batch["image"]), batch["target"])
+    loss.backward()
+    opt.step()
+    third = all_paths(net)
+    assert not torch.equal(third[0], second[0])
+    assert same(third, fresh_paths())
+
+
+def test_input_gradient_request_raises():
+    from floodplanet_code_b200.unet import UNet
+    net = UNet(4, 3).cuda().train()
+    x = torch.rand(1, 4, 32, 32, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="input images"):
+        net(x)

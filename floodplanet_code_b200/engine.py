@@ -274,6 +274,16 @@ class _Schedule:
         self._fold_cache: Dict[str, Tuple[tuple, torch.Tensor, torch.Tensor]] = {}
         self.launches = 0  # kernels launched by the last forward/backward (for bench accounting)
         self.names: List[str] = []
+        # optional debug trace: when a list, every kernel step appends a record {"op": ..., tensors}
+        # holding REFERENCES to the buffers it read and wrote (nothing is copied or recomputed, the
+        # schedule is unchanged).  The teacher-forced parity tests walk it: each step's own inputs are
+        # fed to the fp32 oracle op and compared with the step's own outputs.
+        self.trace: Optional[list] = None
+
+    def _tr(self, op: str, **rec) -> None:
+        if self.trace is not None:
+            rec["op"] = op
+            self.trace.append(rec)
 
     # -------------------------------------------------------------------------------------
     @staticmethod
@@ -353,6 +363,8 @@ class _Schedule:
             fw.launches += 4  # memset+conv counted as conv(2), finalize, apply
             if fw.save:
                 layers.append(LayerSaved(xin, y, scale, shift, mean, invstd))
+            self._tr("conv_bn_relu", spec=s, x=xin, y=y, scale=scale, shift=shift, mean=mean, invstd=invstd,
+                     a=a, pooled=pool_to, pool_idx=(idx if pool_to is not None and not defer_apply else None))
             if defer_apply:
                 return y, scale, shift
         else:
@@ -424,6 +436,7 @@ class _Schedule:
             c = ENC_CH[lvl]
             ops.upsample2x_pad_concat_fwd(cur, cat[lvl][..., c:])
             fw.launches += 1
+            self._tr("upsample_concat", level=lvl, x=cur, cat=cat[lvl], c=c)
             cur = self._conv_bn_relu(fw, specs[li], specs[li].cin, cat[lvl], None, None, layers, None); li += 1
             if lvl == 0 and fw.training and head:
                 # last layer: its normalise+ReLU is fused into the head kernel (forward) and its
@@ -442,6 +455,7 @@ class _Schedule:
         ops.head1x1_fwd(cur, wh, fw.params[f"{head_prefix}outc.conv.bias"].detach(), logits,
                         head_scale, head_shift)
         fw.launches += 1
+        self._tr("head", x=cur, scale=head_scale, shift=head_shift, logits=logits, prefix=head_prefix)
         return logits, cur
 
     # ----------------------------------------------------------------------------- backward
@@ -536,6 +550,9 @@ class _Schedule:
             else:
                 self._timed("dgrad", s, n, hh * ww, lambda: ops.conv3x3_dgrad(dy, wd, dx))
             bw.launches += 1
+        self._tr("layer_bwd", spec=s, da=da, y=sv.y, x=sv.x, dy=dy, dx=dx, coef=coef,
+                 dw=grads[f"{s.conv}.weight"], dgamma=grads[f"{s.bn}.weight"], dbeta=grads[f"{s.bn}.bias"],
+                 fused_reduce=bn_parts is not None)
         self._mark_ready(bw, f"{s.conv}.weight")
         return dx
 
@@ -558,6 +575,9 @@ class _Schedule:
                         parts, bn=(last.scale, last.shift, last.mean, last.invstd),
                         bn_partials=head_bn_parts)
         bw.launches += 2
+        self._tr("head_bwd", dlogits=dlogits, x=head_in, bn=last, d_act=d_cur,
+                 dw=grads[f"{head_prefix}outc.conv.weight"], db=grads[f"{head_prefix}outc.conv.bias"],
+                 prefix=head_prefix)
         self._mark_ready(bw, f"{head_prefix}outc.conv.weight")
 
         li = len(specs) - 1
@@ -574,6 +594,7 @@ class _Schedule:
             d_cur = torch.empty((n, hl, wl, c), **bw.bf)
             ops.upsample2x_pad_concat_bwd(dcat[lvl][..., c:], d_cur)
             bw.launches += 1
+            self._tr("upsample_concat_bwd", level=lvl, dcat=dcat[lvl], c=c, dx=d_cur)
         assert li == -1
         return dcat, d_cur
 
@@ -595,9 +616,12 @@ class _Schedule:
             # the skip layer's BatchNorm-backward reduction rides in the pool-backward pass
             sk = layers[li]
             pool_parts = torch.empty((2 * bw.bn_rows, 2, c), **bw.f32)
-            ops.maxpool2_bwd(d_pool, pool_idx[lvl], d_skip_of(lvl), d_skip, bn_y=sk.y,
+            d_from_skip = d_skip_of(lvl)
+            ops.maxpool2_bwd(d_pool, pool_idx[lvl], d_from_skip, d_skip, bn_y=sk.y,
                              bn=(sk.scale, sk.shift, sk.mean, sk.invstd), bn_partials=pool_parts)
             bw.launches += 1
+            self._tr("maxpool_bwd", level=lvl, d_pooled=d_pool, pool_idx=pool_idx[lvl], d_skip_in=d_from_skip,
+                     d_act=d_skip)
             if release is not None:
                 release(lvl)
             d_mid = self._layer_backward(bw, specs[li], layers[li], specs[li].cin, d_skip, True,

@@ -142,8 +142,12 @@ def _up(x1, x2, sd, prefix, training):
 
 def unet_forward_bf16_emulated(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True):
     """Diagnostic variant of :func:`unet_forward` with the CUDA path's bf16 storage points
-    emulated (see :func:`_conv_bn_relu_bf16`).  The CUDA path must match THIS to ~1e-3; the
-    distance between this and the fp32 reference is pure bf16 rounding, not a kernel error."""
+    emulated (see :func:`_conv_bn_relu_bf16`).  Diagnostic only: two bf16 implementations of this
+    network differ from EACH OTHER by 2-4 % at random init (measured: CUDA path vs this 1.6-3.1 %, stock
+    torch.autocast vs this 4-5 %), because where exactly the roundings fall differs and the network
+    amplifies them; tests assert < 4 % here.  The per-step parity at 1e-2 / 2e-2 is the teacher-forced
+    walk (tests/test_teacher_forced_gpu.py), the end-to-end bound is the measured autocast envelope
+    (tests/golden/autocast_envelope.json)."""
     global _EMULATE_BF16
     _EMULATE_BF16 = True
     try:

@@ -9,6 +9,7 @@ The GPU box has no /root/reference; tests there read only the fixtures.
     python tests/golden/make_golden.py          # everything
     python tests/golden/make_golden.py lf       # only the late-fusion fixture
     python tests/golden/make_golden.py augment  # only the normalise / augment fixture
+    python tests/golden/make_golden.py envelope | trajectory | stitch
 """
 import importlib.util
 import sys
@@ -265,7 +266,135 @@ def augment_case():
     print(f"wrote {OUT / 'augment.pt'}")
 
 
+def _rel(a, b):
+    a, b = a.detach().double().flatten(), b.detach().double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _ref_step(ref_unet, init_sd, batch, c, n_classes, ignore_index, autocast):
+    """One forward + loss + backward of the UNMODIFIED reference module, fp32 or under stock
+    torch.autocast('cpu', bfloat16)."""
+    model = ref_unet.UNet(c, n_classes)
+    model.load_state_dict(init_sd)
+    model.train()
+    if autocast:
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            logits = model(batch["image"])
+            loss = nn.CrossEntropyLoss(ignore_index=ignore_index)(logits.float(), batch["target"])
+    else:
+        logits = model(batch["image"])
+        loss = nn.CrossEntropyLoss(ignore_index=ignore_index)(logits, batch["target"])
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    return logits.detach().float(), float(loss.detach()), grads
+
+
+def envelope_case(only=None):
+    """Third point of the whole-network comparison: how far is ANOTHER bf16 implementation -- the
+    unmodified reference module under stock torch.autocast(bfloat16) -- from the reference's own
+    fp32 result, on the same weights and inputs?  Stored as relative L2 errors (logits, loss, every
+    parameter gradient) in a small JSON; tests/test_envelope_gpu.py asserts that the CUDA path is no
+    further from fp32 than 1.25x this envelope.  Inputs / weights are regenerated from seeds
+    (oracle.synthetic_batch / init_state_dict == torch.manual_seed(s); UNet(...))."""
+    import json
+    sys.path.insert(0, str(OUT.parent.parent))
+    from oracle import unet_oracle as O
+    ref_unet = load_by_path("ref_unet", REF / "models" / "unet.py")
+    # the first three are the inputs / weights of the committed unet_* fixtures above
+    cases = [dict(name="unet_c4_32", n=2, c=4, h=32, w=32, seed=0, block=8),
+             dict(name="unet_c4_44x36", n=1, c=4, h=44, w=36, seed=3, block=8),
+             dict(name="unet_c6_37_ef", n=2, c=6, h=37, w=37, seed=5, block=8, n_classes=2, ignore_index=-100),
+             dict(name="b2_128", n=2, c=4, h=128, w=128, seed=20, block=16),
+             dict(name="b4_256", n=4, c=4, h=256, w=256, seed=21, block=32),
+             dict(name="b2_300", n=2, c=4, h=300, w=300, seed=22, block=20),
+             dict(name="parity_b8_512", n=8, c=4, h=512, w=512, seed=40, block=32)]   # BASELINE.json configs[0]
+    out = {"how": "reference UNet (st_water_seg/models/unet.py) + CrossEntropyLoss(ignore_index=0), CPU; "
+                  "rel = ||autocast - fp32|| / ||fp32||; torch " + torch.__version__,
+           "cases": []}
+    path = OUT / "autocast_envelope.json"
+    if only:                                   # regenerate some cases, keep the others
+        out = json.loads(path.read_text())
+        out["cases"] = [c for c in out["cases"] if c["name"] not in only]
+        cases = [c for c in cases if c["name"] in only]
+    for cs in cases:
+        ncls, ii = cs.setdefault("n_classes", 3), cs.setdefault("ignore_index", 0)
+        torch.manual_seed(cs["seed"])
+        init_sd = {k: v.detach().clone() for k, v in ref_unet.UNet(cs["c"], ncls).state_dict().items()}
+        chk = O.init_state_dict(cs["c"], ncls, seed=cs["seed"])
+        assert all(torch.equal(init_sd[k], chk[k]) for k in init_sd)       # the seeds regenerate the weights
+        batch = O.synthetic_batch(cs["n"], cs["c"], cs["h"], cs["w"], seed=cs["seed"] + 1, block=cs["block"])
+        lg32, loss32, g32 = _ref_step(ref_unet, init_sd, batch, cs["c"], ncls, ii, autocast=False)
+        lg16, loss16, g16 = _ref_step(ref_unet, init_sd, batch, cs["c"], ncls, ii, autocast=True)
+        rec = dict(cs)
+        rec["loss_fp32"] = loss32
+        rec["loss_autocast"] = loss16
+        rec["logits_rel"] = _rel(lg16, lg32)
+        rec["argmax_agree"] = float((lg16.argmax(1) == lg32.argmax(1)).float().mean())
+        rec["grad_rel"] = {k: _rel(g16[k], g32[k]) for k in g32}
+        rec["grad_cos"] = {k: float((g16[k].double().flatten() @ g32[k].double().flatten())
+                                    / (g16[k].double().norm() * g32[k].double().norm()).clamp_min(1e-30)) for k in g32}
+        out["cases"].append(rec)
+        w = [k for k in g32 if k.endswith("weight") and g32[k].dim() == 4]
+        print(f"envelope {cs}: logits {rec['logits_rel']:.4f} loss {loss32:.5f}/{loss16:.5f} "
+              f"grad rel min {min(rec['grad_rel'][k] for k in w):.3f} max {max(rec['grad_rel'][k] for k in w):.3f}")
+    path.write_text(json.dumps(out, indent=1))
+
+
+def trajectory_case(steps=100, n=8, size=64, lr=1e-3, seed=30):
+    """Training trajectory of the UNMODIFIED reference module: Adam (water_seg_model.py:198-205) on a
+    fixed set of 8 chips for 100 steps, in fp32 and under stock torch.autocast(bfloat16); loss per step,
+    final eval-mode confusion counts.  tests/test_trajectory_gpu.py trains the CUDA path on the same
+    chips from the same weights and compares the curves."""
+    import json
+    sys.path.insert(0, str(OUT.parent.parent))
+    from oracle import unet_oracle as O
+    ref_unet = load_by_path("ref_unet", REF / "models" / "unet.py")
+    torch.manual_seed(seed)
+    init_sd = {k: v.detach().clone() for k, v in ref_unet.UNet(4, 3).state_dict().items()}
+    batch = O.synthetic_batch(n, 4, size, size, seed=seed + 1, block=8, ignore_frac=0.5)
+    out = {"cfg": dict(steps=steps, n=n, size=size, lr=lr, seed=seed, ignore_index=-100, ignore_frac=0.5, block=8),
+           "how": "reference UNet + CrossEntropyLoss (no pixel ignored: classes 0 / 1) + optim.Adam(lr), CPU, torch "
+                  + torch.__version__}
+    for mode in ("fp32", "autocast"):
+        torch.manual_seed(0)
+        model = ref_unet.UNet(4, 3)
+        model.load_state_dict(init_sd)
+        opt = torch.optim.Adam(model.parameters(), lr=lr)
+        lossf = nn.CrossEntropyLoss(ignore_index=-100)
+        curve = []
+        for i in range(steps):
+            model.train()
+            opt.zero_grad()
+            if mode == "autocast":
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    loss = lossf(model(batch["image"]).float(), batch["target"])
+            else:
+                loss = lossf(model(batch["image"]), batch["target"])
+            loss.backward()
+            opt.step()
+            curve.append(float(loss.detach()))
+        model.eval()
+        with torch.no_grad():
+            if mode == "autocast":
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    lg = model(batch["image"]).float()
+            else:
+                lg = model(batch["image"])
+        conf = O.confusion_counts(lg.argmax(1).flatten(), batch["target"].flatten(), 3, None)
+        mm = O.micro_metrics(conf, None)
+        out[mode] = {"loss": curve, "eval_loss": float(lossf(lg, batch["target"])), "confusion": conf.tolist(),
+                     "metrics": mm}
+        print(f"trajectory {mode}: loss {curve[0]:.4f} -> {curve[-1]:.4f}, eval loss {out[mode]['eval_loss']:.4f}, {mm}")
+    (OUT / "trajectory.json").write_text(json.dumps(out))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "envelope":
+        envelope_case(sys.argv[2:] or None)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "trajectory":
+        trajectory_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "lf":
         lf_case("lf_c4_dem1_32", {"ms_image": 4, "dem": 1}, n=2, h=32, w=32, n_classes=3, ignore_index=0, seed=11)
         sys.exit(0)
@@ -282,3 +411,5 @@ if __name__ == "__main__":
     tiler_case()
     lf_case("lf_c4_dem1_32", {"ms_image": 4, "dem": 1}, n=2, h=32, w=32, n_classes=3, ignore_index=0, seed=11)
     augment_case()
+    envelope_case()
+    trajectory_case()

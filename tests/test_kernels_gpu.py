@@ -641,6 +641,48 @@ def test_full_size_conv_adjoint_identities(ops, cin, cout, hw):
     assert torch.equal(dw, dw2)
 
 
+@pytest.mark.parametrize("n,hw,cin,cout", [
+    (8, 512, 128, 64),      # up4.conv.double_conv.0: the FLOP-dominant Cout = 64 full-resolution layer
+    (8, 64, 1024, 512),     # up1.conv.double_conv.0: deepest K (9216), 4 channel blocks, persistent wrap-around
+    (16, 256, 64, 128),     # down1 first conv: 8-epilogue-warp variant, one K chunk
+    (8, 512, 16, 64),       # first layer, channel-padded input (KCH = 16), MODE_X_STACK wgrad
+])
+def test_full_size_conv_vs_cudnn_fp32(ops, n, hw, cin, cout):
+    """Full-size fprop / dgrad / wgrad (N >= 8 at the bench resolutions: persistent grids wrap around,
+    split-K wgrad runs with hundreds of splits) against cuDNN in TRUE fp32 on the same GPU (TF32 off in
+    conftest.py) as the checker, on the same bf16 inputs: north_star tolerances 1e-2 / 2e-2."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = (torch.rand(n, hw, hw, cin, generator=g, device="cuda") - 0.3).to(torch.bfloat16)
+    wt = rand_w(cout, cin, 12)
+    dy = (torch.randn(n, hw, hw, cout, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    y = torch.empty(n, hw, hw, cout, dtype=torch.bfloat16, device="cuda")
+    parts = torch.empty(ops.stat_rows(), 2, cout, dtype=torch.float32, device="cuda")
+    ops.conv3x3_fprop(x, ops.repack_fprop(wt, cin), y, stat_partials=parts)
+    dx = torch.empty_like(x)
+    ops.conv3x3_dgrad(dy, ops.repack_dgrad(wt), dx)
+    dw = torch.empty(cout, cin, 3, 3, device="cuda")
+    ws = torch.empty(ops.wgrad_workspace_bytes(n, hw, hw, cin, cout) // 4, device="cuda")
+    ops.conv3x3_wgrad(x, dy, dw, ws, cin)
+    torch.cuda.synchronize()
+    assert not torch.backends.cudnn.allow_tf32 and not torch.backends.cuda.matmul.allow_tf32
+    xf, dyf = nchw(x.float()), nchw(dy.float())
+    del x, dy
+    ref = F.conv2d(xf, wt, padding=1)
+    e_f = rel(nchw(y.float()), ref)
+    s = parts.double().sum(0)
+    e_s = rel(s[1], (ref.double() ** 2).sum((0, 2, 3)))
+    del ref, y
+    ref = torch.nn.grad.conv2d_input(tuple(xf.shape), wt, dyf, padding=1)
+    e_d = rel(nchw(dx.float()), ref)
+    del ref, dx
+    ref = torch.nn.grad.conv2d_weight(xf, tuple(wt.shape), dyf, padding=1)
+    e_w = rel(dw, ref)
+    print(f"\nfull-size {cin}->{cout} @{hw}^2 x{n}: fprop {e_f:.2e} (sum sq {e_s:.1e}) dgrad {e_d:.2e} wgrad {e_w:.2e}")
+    assert e_f < 1e-2 and e_s < 2e-3, (e_f, e_s)
+    assert e_d < 2e-2, e_d
+    assert e_w < 2e-2, e_w
+
+
 def test_full_size_pool_and_elementwise_properties(ops):
     """Batch 64 x 512 x 512 x 64: max-pool of the fused kernel equals pooling its own activation
     output, indices reproduce the pooled values (gather), pool-backward scatters exactly the

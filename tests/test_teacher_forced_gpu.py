@@ -1,0 +1,79 @@
+"""Teacher-forced whole-network parity (GPU): every step of the REAL wired schedule -- all 18
+conv3x3+BN+ReLU layers, 4 max-pools, 4 upsample+pad+concat stages, the 1x1 head and the masked CE,
+forward AND backward -- is checked against the fp32 torch op the reference dispatches to
+(st_water_seg/models/unet.py:6-111, water_seg_model.py:98-107), each fed the CUDA path's OWN stored
+input of that step.  Feeding every oracle op the same (bf16-stored) input the kernel saw removes the
+chaotic amplification of an 18-layer random-init network, so the north_star tolerances apply per
+step: forward <= 1e-2, gradients (dx, dW, dgamma, dbeta) <= 2e-2 relative L2.  Integer outputs
+(max-pool values / argmax) are bit-exact.
+
+The walk also proves the WIRING, which per-kernel tests cannot: each step's input must be (bitwise)
+the tensor the reference graph says it is -- the conv after a pool reads the pooled map, the first conv
+of an Up stage reads cat([skip, upsampled]) with the skip in the LOWER channel half, the pool backward
+adds the skip half of the concat gradient, the upsample backward reads the upper half, BatchNorm
+reductions fused into dgrad / pool-backward / head-backward epilogues feed the right layer.
+
+The engine's trace (engine._Schedule.trace) only records references to the buffers the schedule
+reads and writes; it changes no launch.
+"""
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+from oracle import teacher_forced as TF
+
+pytestmark = pytest.mark.gpu
+
+
+def run_traced(n, c_in, h, w, seed, ignore_index=0, block=32):
+    from floodplanet_code_b200.loss import MaskedCrossEntropyLoss
+    from floodplanet_code_b200.unet import UNet
+    sd = O.init_state_dict(c_in, 3, seed=seed)
+    m = UNet(c_in, 3)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    b = O.synthetic_batch(n, c_in, h, w, seed=seed, block=block, device="cuda")
+    eng = m._engine
+    eng.trace = []
+    try:
+        logits = m(b["image"])
+        loss_fn = MaskedCrossEntropyLoss(ignore_index)
+        loss = loss_fn(logits, b["target"])
+        loss.backward()
+        torch.cuda.synchronize()
+        trace = eng.trace
+    finally:
+        eng.trace = None
+    return m, {k: v.cuda() for k, v in sd.items()}, b, logits.detach(), loss.detach(), trace
+
+
+
+CASES = [
+    # n, c_in, h, w, seed           -- BASELINE.json configs[0] is the first one
+    pytest.param(8, 4, 512, 512, 0, id="parity_config_b8_512"),
+    pytest.param(2, 4, 300, 300, 1, id="default_crop_300"),          # conf/config.yaml:17-18, odd sizes + pad
+    pytest.param(2, 6, 44, 36, 2, id="early_fusion_c6_44x36"),       # ragged patches, padded first layer
+]
+
+
+@pytest.mark.parametrize("n,c_in,h,w,seed", CASES)
+def test_teacher_forced_walk_forward_and_backward(n, c_in, h, w, seed):
+    m, sd0, batch, logits, loss, trace = run_traced(n, c_in, h, w, seed, ignore_index=0,
+                                                    block=32 if h >= 128 else 8)
+    report = TF.walk(m, sd0, batch, logits, loss, trace, 0)
+    worst_f = max((e for k, e in report if k.startswith("fwd")), default=0.0)
+    worst_b = max((e for k, e in report if k.startswith("bwd")), default=0.0)
+    print(f"\nteacher-forced {n}x{c_in}x{h}x{w}: {len(report)} comparisons, worst forward {worst_f:.2e} "
+          f"(tol {TF.FWD_TOL}), worst backward {worst_b:.2e} (tol {TF.GRAD_TOL})")
+    for k, e in sorted(report, key=lambda t: -t[1])[:6]:
+        print(f"   {e:.3e}  {k}")
+    assert len(report) >= 140
+
+
+def test_trace_is_off_by_default_and_costs_nothing():
+    from floodplanet_code_b200.unet import UNet
+    m = UNet(4, 3).cuda().train()
+    assert m._engine.trace is None
+    x = torch.rand(1, 4, 32, 32, device="cuda")
+    out = m(x)
+    assert m._engine.trace is None and out.shape == (1, 3, 32, 32)

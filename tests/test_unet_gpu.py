@@ -18,22 +18,20 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 
 LOGIT_TOL = 1e-2      # north_star: logits / loss within 1e-2 relative of the fp32 reference
 GRAD_TOL = 2e-2       # north_star: gradients within 2e-2 relative
-# Whole-network envelope.  A randomly initialised 18-layer BatchNorm/ReLU network amplifies ANY
-# perturbation ~40x from input to logits, so storing activations in bf16 (2^-9 relative
-# rounding per element, what "bf16 compute, fp32 accumulate" means) moves the logits ~4-5% away
-# from the fp32 reference no matter how exact the kernels are: the fp32-arithmetic oracle with
-# only the bf16 STORAGE points emulated (oracle.unet_forward_bf16_emulated) sits at the same
-# distance.  The 1e-2 / 2e-2 bars are therefore asserted where inputs are identical (per
-# kernel in test_kernels_gpu.py, per DoubleConv block below) and on the loss; end to end we
-# assert that the CUDA path is as close to the fp32 reference as the emulated-bf16 reference.
-NET_LOGIT_ENVELOPE = 8e-2
+# Where each bar is asserted:
+#   * 1e-2 / 2e-2 per step of the REAL wired network, forward and backward, every parameter gradient,
+#     each oracle op fed the CUDA path's own input: tests/test_teacher_forced_gpu.py;
+#   * 1e-2 on the loss end to end: here;
+#   * end-to-end logits / gradients: a randomly initialised 18-layer BatchNorm/ReLU network amplifies
+#     ANY perturbation ~40x, so a bf16-activation implementation sits 4-6 % from the fp32 logits no
+#     matter how exact its kernels are.  The envelope is MEASURED, not argued: the unmodified reference
+#     module under stock torch.autocast(bfloat16) against its own fp32 result
+#     (tests/golden/autocast_envelope.json, made from /root/reference by make_golden.py); the CUDA path
+#     must be within ENVELOPE_FACTOR of it, logits and every parameter gradient (also
+#     tests/test_envelope_gpu.py at 128^2 .. 8 x 512^2).
+ENVELOPE_FACTOR = 1.25
+NET_LOGIT_ENVELOPE = 8e-2     # only for inputs without a stored envelope (eval / odd-size smoke checks)
 NET_VS_EMULATED = 4e-2
-# Gradients additionally pass through the ReLU mask, which is DIScontinuous: an activation that
-# lands on the other side of zero after a 2^-9 rounding flips its whole gradient on or off, so
-# a fraction p ~ 0.3% of flipped masks costs sqrt(p) ~ 5% relative L2 per layer against the
-# fp32 reference, compounding through 18 layers.  Gradients therefore meet the 2e-2 bar where
-# pre-activations are identical (kernel tests, the DoubleConv block test below, the layers
-# next to the loss) and are checked by direction / magnitude end to end.
 
 
 def rel(a, b):
@@ -44,6 +42,12 @@ def rel(a, b):
 
 def load(name):
     return torch.load(GOLDEN / f"{name}.pt", weights_only=False)
+
+
+def envelope(name):
+    import json
+    cases = json.loads((GOLDEN / "autocast_envelope.json").read_text())["cases"]
+    return {c["name"]: c for c in cases}[name]
 
 
 def build(cfg):
@@ -80,8 +84,9 @@ def test_train_step_matches_reference_golden(name):
     inherent = rel(emu, fx["logits_train"])
     print(f"{name}: logits vs fp32 ref {e_fp32:.4f}, vs bf16-emulated ref {e_emu:.4f}, "
           f"emulated vs fp32 {inherent:.4f}")
-    assert e_fp32 < NET_LOGIT_ENVELOPE, f"logits rel err {e_fp32}"
-    assert e_fp32 < 1.5 * inherent + LOGIT_TOL, (e_fp32, inherent)
+    env = envelope(name)
+    assert abs(env["loss_fp32"] - fx["loss"]) <= 1e-5 * abs(fx["loss"])     # same run of the reference
+    assert e_fp32 <= ENVELOPE_FACTOR * env["logits_rel"], (e_fp32, env["logits_rel"])
     assert e_emu < NET_VS_EMULATED, f"logits vs bf16-emulated reference {e_emu}"
     # (2) loss within the north_star tolerance of the reference's loss
     loss_fn = MaskedCrossEntropyLoss(ignore_index=cfg["ignore_index"])
@@ -101,10 +106,12 @@ def test_train_step_matches_reference_golden(name):
             layer_w = k[:-4] + "weight"
             assert float(got.abs().max()) <= 1e-4 * float(ograds[layer_w].abs().max()) + 1e-12, k
             continue
-        a, b = got.detach().double().flatten().cpu(), g.double().flatten()
-        cos = float(a @ b / (a.norm() * b.norm()).clamp_min(1e-30))
-        ratio = float(a.norm() / b.norm().clamp_min(1e-30))
-        assert cos > 0.75 and 0.8 < ratio < 1.25, (k, cos, ratio)
+        # every parameter gradient inside the measured bf16 envelope of the reference itself
+        e = rel(got, g)
+        assert e <= ENVELOPE_FACTOR * env["grad_rel"][k] + 2e-3, (k, e, env["grad_rel"][k])
+        # ... and against the reference's own stored gradient summary (norm within the same envelope)
+        assert abs(float(got.double().norm()) - fx["grads"][k]["norm"]) <= \
+            (ENVELOPE_FACTOR * env["grad_rel"][k] + 2e-3) * fx["grads"][k]["norm"], k
     # the layers nearest the loss see un-amplified inputs: there the 2e-2 bar holds end to end
     for k in ("outc.conv.weight", "outc.conv.bias", "up4.conv.double_conv.4.weight",
               "up4.conv.double_conv.4.bias"):
@@ -342,6 +349,9 @@ def test_parity_config_batch8_512():
     named = dict(m.named_parameters())
     for k in ("outc.conv.weight", "outc.conv.bias", "up4.conv.double_conv.4.weight", "up4.conv.double_conv.4.bias"):
         assert rel(named[k].grad, ograds[k]) < GRAD_TOL, k
+    # (every step / every parameter gradient of this configuration at 1e-2 / 2e-2: the teacher-forced walk,
+    # test_teacher_forced_gpu.py::parity_config_b8_512; end to end inside the reference's own bf16 envelope:
+    # test_envelope_gpu.py::parity_b8_512)
     # size-independent properties at full size: BN partial statistics are consistent
     # (running_var stays positive / finite) and every gradient is finite
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())

@@ -8,7 +8,9 @@ Restates, for the inference configuration (BASELINE.json configs[4]):
     (st_water_seg/utils/utils_image.py:410-494),
   * infer.py's post-processing: softmax over classes (:123), stitch (:160-163),
     ``np.clip(argmax, 0, 1) * 255`` as uint8 (:181-184).
-Pinned against the reference functions imported by path in ``tests/golden/make_golden.py``.
+Pinned against the reference itself: ``tests/golden/make_golden.py`` imports ``datasets/utils.py`` (tiler,
+CropParams) and ``utils/utils_image.py`` (ImageStitcher_v2) by file path and stores their outputs
+(``tests/golden/tiler.pt``, ``stitch.pt``); ``tests/test_oracle.py`` checks this module against them.
 """
 from __future__ import annotations
 

@@ -11,4 +11,4 @@ python -m pytest tests -q -m gpu -x > gpurun_out/r2_t_all.log 2>&1
 echo "all rc=$?" >> gpurun_out/r2_t_all.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/r2_smoke.log
-tail -5 gpurun_out/r2_t_new.log gpurun_out/r2_t_fullsize.log gpurun_out/r2_t_all.log gpurun_out/r2_smoke.log
+for f in gpurun_out/r2_t_new.log gpurun_out/r2_t_fullsize.log gpurun_out/r2_t_all.log gpurun_out/r2_smoke.log; do echo "== $f"; tail -n 5 $f; done

@@ -266,6 +266,51 @@ def augment_case():
     print(f"wrote {OUT / 'augment.pt'}")
 
 
+def stitch_case():
+    """Outputs of the reference's OWN `ImageStitcher_v2.add_image / get_combined_images`
+    (utils/utils_image.py:364-494,569-571) and of infer.py's mask rule (:181-184) for tile sets made by
+    the reference's own `get_crop_slices` + `CropParams` (datasets/utils.py:22-52,86-212): a stride = crop
+    case, a ragged one and an overlapping one.  `utils_image.py` is loaded by file path with a stand-in
+    for `tifffile` (only used by save_images, not by the arithmetic under test)."""
+    import tempfile
+    import numpy as np
+    tf = types.ModuleType("tifffile"); tf.tifffile = types.ModuleType("tifffile.tifffile")
+    sys.modules.setdefault("tifffile", tf); sys.modules.setdefault("tifffile.tifffile", tf.tifffile)
+    hydra = types.ModuleType("hydra"); hydra.utils = types.ModuleType("hydra.utils")
+    hydra.utils.get_original_cwd = lambda: "."
+    sys.modules.setdefault("hydra", hydra); sys.modules.setdefault("hydra.utils", hydra.utils)
+    ui = load_by_path("ref_utils_image", REF / "utils" / "utils_image.py")
+    du = load_by_path("ref_ds_utils2", REF / "datasets" / "utils.py")
+    cases = []
+    for (H, W, crop, stride, ncls, seed) in [(96, 64, 32, 32, 3, 1), (100, 70, 32, 32, 3, 2), (80, 112, 32, 16, 3, 3),
+                                              (75, 75, 30, 15, 2, 4)]:
+        tiles = du.get_crop_slices(H, W, crop, crop, stride, mode="exact")
+        rng = np.random.RandomState(seed)
+        with tempfile.TemporaryDirectory() as td:
+            st = ui.ImageStitcher_v2(td, save_backend="tifffile", save_ext=".tif")
+            preds = []
+            for (h0, w0, hh, ww) in tiles:
+                # what infer.py:122-127 hands the stitcher: softmax over classes of a full crop-sized output
+                lg = rng.standard_normal((ncls, crop, crop)).astype(np.float32) * 2
+                from scipy.special import softmax
+                pred = softmax(lg[None], axis=1)[0].transpose(1, 2, 0)          # infer.py:123,127
+                preds.append(lg)
+                cp = du.CropParams(h0, w0, hh, ww, H, W, crop, crop)
+                st.add_image(pred, "scene", cp, H, W)
+            canvas = st.get_combined_images()["scene"]
+        mask = (np.clip(canvas.argmax(axis=2), 0, 1) * 255).astype("uint8")      # infer.py:181-184
+        cases.append({"H": H, "W": W, "crop": crop, "stride": stride, "n_classes": ncls, "seed": seed,
+                      "tiles": [list(map(int, t)) for t in tiles],
+                      # logits are regenerated in the test: RandomState(seed).standard_normal((ncls, crop, crop))
+                      # .astype(float32) * 2 per tile, in tile order
+                      "logits_checksum": float(np.stack(preds).astype(np.float64).sum()),
+                      "canvas": torch.from_numpy(np.asarray(canvas)), "mask": torch.from_numpy(mask)})
+        print(f"stitch case {H}x{W} crop {crop} stride {stride}: {len(tiles)} tiles, canvas {canvas.dtype}, "
+              f"water fraction {(mask > 0).mean():.3f}")
+    torch.save({"cases": cases}, OUT / "stitch.pt")
+    print("wrote", OUT / "stitch.pt", (OUT / "stitch.pt").stat().st_size, "bytes")
+
+
 def _rel(a, b):
     a, b = a.detach().double().flatten(), b.detach().double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
@@ -392,6 +437,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "envelope":
         envelope_case(sys.argv[2:] or None)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "stitch":
+        stitch_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "trajectory":
         trajectory_case()
         sys.exit(0)
@@ -413,3 +461,4 @@ if __name__ == "__main__":
     augment_case()
     envelope_case()
     trajectory_case()
+    stitch_case()

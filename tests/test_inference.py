@@ -71,3 +71,32 @@ def test_tile_sharding_is_a_partition_of_the_single_gpu_result():
     assert sum(p[1] for p in parts) == n == 12
     merged = torch.stack([p[0] for p in parts]).max(0).values
     assert torch.equal(merged, full)
+
+
+@pytest.mark.gpu
+def test_device_stitch_kernels_match_reference_stitcher_golden():
+    """softmax_stitch_add + canvas_to_mask_u8 on the logits of tests/golden/stitch.pt against the outputs
+    of the reference's OWN ImageStitcher_v2 + infer.py mask rule stored there."""
+    from floodplanet_code_b200 import ops
+    fx = torch.load(GOLDEN / "stitch.pt", weights_only=False)
+    for cs in fx["cases"]:
+        H, W, crop, stride, ncls = cs["H"], cs["W"], cs["crop"], cs["stride"], cs["n_classes"]
+        tiles = cs["tiles"]
+        rng = np.random.RandomState(cs["seed"])
+        logits = np.stack([rng.standard_normal((ncls, crop, crop)).astype(np.float32) * 2 for _ in tiles])
+        assert float(logits.astype(np.float64).sum()) == cs["logits_checksum"]
+        meta = [[h0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in tiles]
+        tdev = torch.tensor(meta, dtype=torch.int32, device="cuda")
+        canvas = torch.zeros((H, W, ncls), dtype=torch.float32, device="cuda")
+        weight = torch.zeros((H, W), dtype=torch.float32, device="cuda")
+        ops.softmax_stitch_add(torch.from_numpy(logits).cuda(), canvas, weight, tdev)
+        mask = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+        ops.canvas_to_mask_u8(canvas, weight, mask)
+        want_canvas = cs["canvas"].numpy()
+        got_canvas = (canvas.double() / (weight.double()[:, :, None] + 1e-5)).cpu().numpy()
+        assert np.abs(got_canvas - want_canvas).max() < 2e-6          # fp32 exp / summation order
+        got, want = mask.cpu().numpy(), cs["mask"].numpy()
+        if stride == crop:
+            assert np.array_equal(got, want)
+        else:
+            assert (got != want).mean() < 2e-3

@@ -139,3 +139,25 @@ def test_encode_decode_compose_to_forward():
         a = O.unet_forward(sd, x, training=False)
         b = O.unet_decode(sd, O.unet_encode(sd, x, training=False), training=False)
     assert torch.equal(a, b)
+
+
+def test_stitch_oracle_matches_reference_image_stitcher_golden():
+    """oracle/tiling_oracle.py (tiler + softmax + Stitcher + mask rule) against outputs of the reference's
+    OWN ImageStitcher_v2 / get_crop_slices / CropParams and scipy softmax (tests/golden/stitch.pt, made by
+    make_golden.py stitch): canvas to 1e-12, uint8 mask bit-exact -- stride = crop, ragged and overlapping."""
+    fx = load("stitch")
+    for cs in fx["cases"]:
+        H, W, crop, stride, ncls = cs["H"], cs["W"], cs["crop"], cs["stride"], cs["n_classes"]
+        tiles = T.crop_slices_exact(H, W, crop, crop, stride)
+        assert tiles == cs["tiles"]
+        rng = np.random.RandomState(cs["seed"])
+        logits = [rng.standard_normal((ncls, crop, crop)).astype(np.float32) * 2 for _ in tiles]
+        assert float(np.stack(logits).astype(np.float64).sum()) == cs["logits_checksum"]
+        st = T.Stitcher(H, W, ncls)
+        for lg, (h0, w0, hh, ww) in zip(logits, tiles):
+            st.add(T.softmax_np(lg[None], axis=1)[0].transpose(1, 2, 0), h0, w0, hh, ww)
+        canvas = st.combined()
+        want = cs["canvas"].numpy()
+        assert canvas.dtype == want.dtype and np.array_equal(canvas, want)     # bit-exact, scipy softmax included
+        mask = T.scene_mask_from_logits(logits, tiles, H, W)
+        assert np.array_equal(mask, cs["mask"].numpy())

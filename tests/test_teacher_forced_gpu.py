@@ -67,6 +67,11 @@ def test_teacher_forced_walk_forward_and_backward(n, c_in, h, w, seed):
           f"(tol {TF.FWD_TOL}), worst backward {worst_b:.2e} (tol {TF.GRAD_TOL})")
     for k, e in sorted(report, key=lambda t: -t[1])[:6]:
         print(f"   {e:.3e}  {k}")
+    from pathlib import Path
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    if out.is_dir():                     # full per-step table for profiles/ (scratch dir, GPU box only)
+        (out / f"teacher_forced_{n}x{c_in}x{h}x{w}.txt").write_text(
+            "".join(f"{e:.4e}  {k}\n" for k, e in report))
     assert len(report) >= 140
 
 

@@ -19,7 +19,7 @@ LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libfloodplanet_b200.so"
 INCLUDE = PKG_DIR.parent / "include"
 
-SOURCES = ["conv_igemm.cu", "conv_igemm_v1.cu", "conv_wgrad.cu", "elementwise.cu", "head_ce.cu", "fusion.cu",
+SOURCES = ["conv_igemm.cu", "conv_wgrad.cu", "elementwise.cu", "head_ce.cu", "fusion.cu",
            "augment.cu"]
 
 NVCC_FLAGS = [
@@ -79,5 +79,28 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+TEST_SRC = PKG_DIR.parent / "tests" / "csrc" / "conv_pertap_crosscheck.cu"
+TEST_LIB_PATH = PKG_DIR.parent / "tests" / "lib" / "libfpb200_crosscheck.so"
+
+
+def build_test_library(force: bool = False) -> Path:
+    """TEST-ONLY: the first-generation per-tap conv kernel as its own shared library
+    (tests/lib/libfpb200_crosscheck.so).  The product library neither contains nor exports it."""
+    if not TEST_SRC.exists():
+        raise RuntimeError(f"{TEST_SRC} missing")
+    deps = [TEST_SRC, CSRC / "ptx.cuh", CSRC / "host_common.h", INCLUDE / "floodplanet_b200.h"]
+    if (not force and TEST_LIB_PATH.exists()
+            and all(d.stat().st_mtime <= TEST_LIB_PATH.stat().st_mtime for d in deps)):
+        return TEST_LIB_PATH
+    TEST_LIB_PATH.parent.mkdir(exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(INCLUDE), "-I", str(CSRC), "-shared", str(TEST_SRC), "-o",
+           str(TEST_LIB_PATH), "-cudart", "static"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {TEST_SRC.name}:\n{res.stdout}\n{res.stderr}")
+    return TEST_LIB_PATH
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_test_library(force="--force" in sys.argv))

@@ -25,7 +25,6 @@ SIGNATURES = {
     "fpb200_repack_weights_batch": (_i, [_vp, _i, _l, _vp]),
     "fpb200_conv_stat_rows": (_i, []),
     "fpb200_conv3x3_fprop_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
-    "fpb200_conv3x3_pertap_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "fpb200_conv3x3_dgrad_bf16_nhwc": (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp, _vp,
                                             _vp, _vp]),
     "fpb200_conv3x3_wgrad_workspace_bytes": (_l, [_i, _i, _i, _i, _i]),

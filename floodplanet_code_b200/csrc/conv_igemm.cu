@@ -44,11 +44,6 @@
 #include "ptx.cuh"
 
 namespace fp {
-namespace v1 {
-int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, long ldy, int N, int H,
-                     int W, int Cin, int Cout, const float* scale, const float* shift, int relu,
-                     float* stat_partials, cudaStream_t stream);
-}
 
 
 struct HaloParams {
@@ -548,14 +543,6 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
 }  // namespace fp
 
 extern "C" {
-
-int fpb200_conv3x3_pertap_bf16_nhwc(const void* x, long ldx, const void* w_packed, void* y, long ldy,
-                                    int N, int H, int W, int Cin, int Cout, const float* scale,
-                                    const float* shift, int relu, float* stat_partials,
-                                    void* stream) {
-  return fp::v1::conv3x3_dispatch(x, ldx, w_packed, y, ldy, N, H, W, Cin, Cout, scale, shift, relu,
-                                  stat_partials, static_cast<cudaStream_t>(stream));
-}
 
 int fpb200_conv_stat_rows(void) { return 8 * fp::sm_count(); }
 

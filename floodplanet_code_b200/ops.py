@@ -130,9 +130,8 @@ def repack_dgrad(w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
 
 def conv3x3_fprop(x: torch.Tensor, w_packed: torch.Tensor, y: torch.Tensor,
                   scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
-                  relu: bool = False, stat_partials: Optional[torch.Tensor] = None,
-                  per_tap_kernel: bool = False) -> None:
-    """`per_tap_kernel` selects the first-generation kernel (test cross-check only)."""
+                  relu: bool = False, stat_partials: Optional[torch.Tensor] = None, _fn=None) -> None:
+    """`_fn`: a C function with the same prototype to call instead (the test-only cross-check kernel)."""
     _require_cuda(x, w_packed, y)
     xp, ldx = nhwc_view(x)
     yp, ldy = nhwc_view(y)
@@ -140,7 +139,7 @@ def conv3x3_fprop(x: torch.Tensor, w_packed: torch.Tensor, y: torch.Tensor,
     cout = y.shape[3]
     if w_packed.shape != (cout, 9, cin):
         raise RuntimeError(f"conv3x3_fprop: packed weight {tuple(w_packed.shape)} != ({cout}, 9, {cin})")
-    fn = _lib().fpb200_conv3x3_pertap_bf16_nhwc if per_tap_kernel else _lib().fpb200_conv3x3_fprop_bf16_nhwc
+    fn = _fn if _fn is not None else _lib().fpb200_conv3x3_fprop_bf16_nhwc
     st = fn(xp, ldx, w_packed.data_ptr(), yp, ldy, n, h, w, cin, cout, _ptr(scale), _ptr(shift),
             int(relu), _ptr(stat_partials), _stream())
     capi.check(st, "conv3x3_fprop_bf16_nhwc", N=n, H=h, W=w, Cin=cin, Cout=cout)

@@ -90,15 +90,6 @@ int fpb200_conv3x3_fprop_bf16_nhwc(const void* x, long ldx, const void* w_packed
                                    const float* scale, const float* shift, int relu,
                                    float* stat_partials, void* stream);
 
-/* Same contract as fpb200_conv3x3_fprop_bf16_nhwc, computed by the first-generation kernel (one
- * TMA box per filter tap, per-thread global stores, statistics from the fp32 accumulators).
- * Not used by the product path; kept as an independent in-library cross-check of the halo
- * kernel (tests/test_kernels_gpu.py runs every conv case through both). */
-int fpb200_conv3x3_pertap_bf16_nhwc(const void* x, long ldx, const void* w_packed, void* y,
-                                    long ldy, int N, int H, int W, int Cin, int Cout,
-                                    const float* scale, const float* shift, int relu,
-                                    float* stat_partials, void* stream);
-
 /* dx = conv3x3_transpose(dy, w): Cout channels in, Cin (multiple of 64) channels out.
  * Optional fused BatchNorm-backward reduction (bn_y != NULL): when dx is the gradient w.r.t. the
  * activation a = relu(bn(y_prev)) of the preceding conv layer, pass that layer's raw output

@@ -1,5 +1,7 @@
-// FIRST-GENERATION kernel (one TMA box per filter tap), kept as the small-footprint reference
-// implementation the halo kernel in conv_igemm.cu is validated against.
+// TEST-ONLY cross-check, NOT part of the product library: the first-generation conv kernel (one TMA box
+// per filter tap), built into tests/lib/libfpb200_crosscheck.so by floodplanet_code_b200.build
+// .build_test_library() and loaded only by tests/test_kernels_gpu.py, which runs every fprop case
+// through the product's halo kernel AND this independent implementation.
 //
 // 3x3 / pad 1 / stride 1 convolution as an implicit GEMM on the sm_100a tensor cores.
 //
@@ -349,7 +351,7 @@ int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, lon
   rc = make_tmap_mat(&tmB, w_packed, Cout, 9L * Cin, KCH, BN);
   if (rc != FPB200_OK) return rc;
   if (stat_partials != nullptr) {
-    if (cudaMemsetAsync(stat_partials, 0, (size_t)fpb200_conv_stat_rows() * 2 * Cout * sizeof(float),
+    if (cudaMemsetAsync(stat_partials, 0, (size_t)(8 * sm_count()) * 2 * Cout * sizeof(float),
                         stream) != cudaSuccess)
       return check_launch("conv3x3 stat memset");
   }
@@ -370,3 +372,11 @@ int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void* y, lon
 
 }  // namespace v1
 }  // namespace fp
+
+extern "C" int fpb200_test_conv3x3_pertap_bf16_nhwc(const void* x, long ldx, const void* w_packed, void* y,
+                                                    long ldy, int N, int H, int W, int Cin, int Cout,
+                                                    const float* scale, const float* shift, int relu,
+                                                    float* stat_partials, void* stream) {
+  return fp::v1::conv3x3_dispatch(x, ldx, w_packed, y, ldy, N, H, W, Cin, Cout, scale, shift, relu,
+                                  stat_partials, static_cast<cudaStream_t>(stream));
+}

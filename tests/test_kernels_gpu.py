@@ -23,9 +23,18 @@ def ops():
 
 @pytest.fixture(params=["halo", "per_tap"])
 def conv_impl(request):
-    """Both conv generations stay under test: the halo kernel (product path) and the
-    first-generation one-box-per-tap kernel kept in the library as its cross-check."""
-    return request.param == "per_tap"
+    """Every fprop case runs through the product's halo kernel AND through an independent
+    implementation: the first-generation one-box-per-tap kernel, built as a TEST-ONLY library
+    (tests/csrc/conv_pertap_crosscheck.cu -> tests/lib/libfpb200_crosscheck.so); the product library
+    does not contain it.  Returns the `_fn` argument of ops.conv3x3_fprop (None = product kernel)."""
+    if request.param == "halo":
+        return None
+    import ctypes as C
+    from floodplanet_code_b200 import build, capi
+    lib = C.CDLL(str(build.build_test_library()))
+    fn = lib.fpb200_test_conv3x3_pertap_bf16_nhwc
+    fn.restype, fn.argtypes = capi.SIGNATURES["fpb200_conv3x3_fprop_bf16_nhwc"]
+    return fn
 
 
 def rel(a, b):
@@ -74,7 +83,7 @@ def test_conv3x3_fprop_and_stats(ops, conv_impl, n, h, w, cin, cout):
     wp = ops.repack_fprop(wt, cin)
     y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
     parts = torch.empty(ops.stat_rows(), 2, cout, dtype=torch.float32, device="cuda")
-    ops.conv3x3_fprop(x, wp, y, stat_partials=parts, per_tap_kernel=conv_impl)
+    ops.conv3x3_fprop(x, wp, y, stat_partials=parts, _fn=conv_impl)
     torch.cuda.synchronize()
     ref = F.conv2d(nchw(x.float()), wt, padding=1)
     err = rel(nchw(y.float()), ref)
@@ -95,7 +104,7 @@ def test_conv3x3_fprop_affine_relu_into_concat_view(ops, conv_impl, n, h, w, cin
     scale = torch.rand(cout, generator=g, device="cuda") + 0.5
     shift = torch.randn(cout, generator=g, device="cuda") * 0.2
     buf = torch.full((n, h, w, 2 * cout), 7.0, dtype=torch.bfloat16, device="cuda")
-    ops.conv3x3_fprop(x, wp, buf[..., :cout], scale=scale, shift=shift, relu=True, per_tap_kernel=conv_impl)
+    ops.conv3x3_fprop(x, wp, buf[..., :cout], scale=scale, shift=shift, relu=True, _fn=conv_impl)
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(nchw(x.float()), wt, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
     assert rel(nchw(buf[..., :cout].float()), ref) < 1e-2

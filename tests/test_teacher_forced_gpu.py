@@ -24,6 +24,15 @@ from oracle import teacher_forced as TF
 
 pytestmark = pytest.mark.gpu
 
+# Tolerances actually asserted: TIGHTER than the north_star's 1e-2 / 2e-2.  Every compared tensor is
+# stored in bf16 (relative rounding 2^-9 / sqrt(3) ~ 1.7e-3 in L2), dgrad additionally uses bf16 weights:
+# measured on B200 the worst forward step is 2.5e-3 and the worst backward step 2.4e-3 in all three cases
+# (profiles/r02_parity.md).  At 5e-3 a 5 % error in ONE BatchNorm-backward coefficient of ONE layer
+# fails the walk (tests/test_teacher_forced_walker_cpu.py).
+TIGHT_FWD_TOL = 5e-3
+TIGHT_GRAD_TOL = 5e-3
+assert TIGHT_FWD_TOL <= TF.FWD_TOL and TIGHT_GRAD_TOL <= TF.GRAD_TOL
+
 
 def run_traced(n, c_in, h, w, seed, ignore_index=0, block=32):
     from floodplanet_code_b200.loss import MaskedCrossEntropyLoss
@@ -60,11 +69,12 @@ CASES = [
 def test_teacher_forced_walk_forward_and_backward(n, c_in, h, w, seed):
     m, sd0, batch, logits, loss, trace = run_traced(n, c_in, h, w, seed, ignore_index=0,
                                                     block=32 if h >= 128 else 8)
-    report = TF.walk(m, sd0, batch, logits, loss, trace, 0)
+    report = TF.walk(m, sd0, batch, logits, loss, trace, 0, fwd_tol=TIGHT_FWD_TOL, grad_tol=TIGHT_GRAD_TOL)
     worst_f = max((e for k, e in report if k.startswith("fwd")), default=0.0)
     worst_b = max((e for k, e in report if k.startswith("bwd")), default=0.0)
     print(f"\nteacher-forced {n}x{c_in}x{h}x{w}: {len(report)} comparisons, worst forward {worst_f:.2e} "
-          f"(tol {TF.FWD_TOL}), worst backward {worst_b:.2e} (tol {TF.GRAD_TOL})")
+          f"(asserted {TIGHT_FWD_TOL}, north_star {TF.FWD_TOL}), worst backward {worst_b:.2e} "
+          f"(asserted {TIGHT_GRAD_TOL}, north_star {TF.GRAD_TOL})")
     for k, e in sorted(report, key=lambda t: -t[1])[:6]:
         print(f"   {e:.3e}  {k}")
     from pathlib import Path

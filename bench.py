@@ -127,10 +127,24 @@ def cpu_reference_chips_per_sec(batch: int, size: int, steps: int, warmup: int, 
 
 
 def run_reference(args):
+    """Reference arm: the reference algorithm (oracle port -- /root/reference does not exist on the GPU
+    box and needs pytorch_lightning etc.) on ALL host cores.  `config` is this
+    repo's arm's config (the workload both arms are quoted on); each step is a bounded SAMPLE of that
+    workload: `--cpu-sample-batch` chips (default 8 = SURVEY.md 8d / BASELINE configs[0]) instead of the
+    per-GPU batch of 64 -- chips/s is batch-normalised.  If the first step says the whole run would not
+    finish in ~6 minutes the sample is halved (stated in `reference_sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sample = args.cpu_sample_batch
+    budget_s = 360.0
+    while True:
+        t0 = time.perf_counter()
+        cpu_reference_chips_per_sec(sample, args.size, 1, 0, args.channels)
+        probe = time.perf_counter() - t0
+        if sample <= 1 or probe * (args.steps + args.warmup) <= budget_s:
+            break
+        sample = max(1, sample // 2)
     best, mean, cores, times = cpu_reference_chips_per_sec(sample, args.size, args.steps, args.warmup,
                                                             args.channels)
     ms = 1000.0 * sum(times) / len(times)
@@ -145,6 +159,11 @@ def run_reference(args):
                                    f"{args.warmup} warm-up (mean; best {best:.4f})"},
         "e2e": {"value": mean, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # the truth about what one step of THIS arm processed (config above is the shared workload)
+        "reference_sample": {"chips_per_step": sample, "requested": args.cpu_sample_batch,
+                             "probe_s_per_step": probe, "precision": "fp32", "host_threads": cores,
+                             "note": "config.per_gpu_batch is the workload's; this arm steps on "
+                                     f"{sample}-chip samples of it (chips/s is batch-normalised)"},
     }
     print(json.dumps(line), flush=True)
 
@@ -163,6 +182,115 @@ def workload_config(args, world):
               f"{args.batch * args.channels * args.size * args.size * 4 / 1e6:.0f} MB image batch and >30 GB of "
               "activations, far beyond the 126 MB L2",
     }
+
+
+# ------------------------------------------------------------------------------------------
+def data_parallel_check(model, reducer, dev, rank, world, args):
+    """Before timing, at the launched world size: the all-reduced gradient slab must be (a) bit-identical
+    on every rank and (b) the MEAN of the ranks' local gradients.  (b) uses linearity: the checksum of
+    the reduced slab equals the mean of the local checksums.  One forward/backward with the hooks off
+    (local), one with them on (reduced), same per-rank batch; kernels are deterministic."""
+    import torch.distributed as dist
+    engine = model.model._engine
+    n = max(2, min(8, args.batch))
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    img = torch.rand(n, args.channels, 128, 128, generator=g, device=dev)
+    tgt = (torch.rand(n, 128, 128, generator=g, device=dev) > 0.5).long()
+    batch = {"image": img, "target": tgt}
+    running = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+
+    def slab_of():
+        for p in model.parameters():
+            p.grad = None
+        model.training_step(batch, 0).backward()
+        return torch.cat([p.grad.detach().double().flatten() for p in model.model.parameters()])
+
+    hooks = (engine.grad_ready_hook, engine.grad_done_hook)
+    engine.grad_ready_hook = engine.grad_done_hook = None
+    local = slab_of()
+    engine.grad_ready_hook, engine.grad_done_hook = hooks
+    reduced = slab_of()
+    torch.cuda.synchronize(dev)
+    w = torch.arange(1, local.numel() + 1, device=dev, dtype=torch.float64).remainder_(97.0).add_(1.0)
+    mine = torch.stack([local.sum(), (local * w).sum(), reduced.sum(), (reduced * w).sum(), reduced.abs().sum()])
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    allv = torch.stack(allv).cpu()
+    identical = bool((allv[:, 2:] == allv[0, 2:]).all())
+    scale = float(allv[0, 4])
+    err = max(abs(float(allv[:, 0].mean() - allv[0, 2])), abs(float(allv[:, 1].mean() - allv[0, 3])) / 49.0) / max(scale, 1e-30)
+    with torch.no_grad():                      # the check must not leave a trace in the timed model
+        sd = model.state_dict()
+        for k, v in running.items():
+            sd[k].copy_(v)
+    for p in model.parameters():
+        p.grad = None
+    from floodplanet_code_b200.engine import note_raw_parameter_write
+    note_raw_parameter_write()
+    ok = identical and err < 1e-6
+    if not ok:
+        raise RuntimeError(f"data-parallel gradient check failed: identical={identical} err={err:.3e}")
+    return {"ranks": world, "reduced_slab_identical_on_all_ranks": identical,
+            "mean_of_local_checksums_rel_err": err, "buckets": reducer.buckets_last_step}
+
+
+def infer_block(model, dev, rank, world, args):
+    """BASELINE.json configs[4]: sliding-window inference over ONE synthetic scene (default 10240 x 10240 x
+    C fp32, 400 tiles of 512, stride = crop as infer.py:64-65), tiles sharded over the launched ranks,
+    END TO END: the scene lives in pinned HOST memory, every timed pass copies each rank's row band to the
+    device, runs eval-mode UNet + softmax + stitch + argmax/clip on the device and brings the uint8 mask back
+    to rank 0's host memory (infer.py:112-184).  Time = max over ranks, CUDA events + host clock."""
+    import torch.distributed as dist
+    from floodplanet_code_b200.inference import crop_slices, predict_scene_from_host
+    from floodplanet_code_b200.parallel import shard_range
+    S, crop, C = args.infer_scene, args.size, args.channels
+    tiles = crop_slices(S, S, crop, crop, crop)
+    mine = [tiles[i] for i in shard_range(len(tiles), rank, world)]
+    scene = torch.empty((C, S, S), dtype=torch.float32, pin_memory=True)
+    if mine:                                   # only this rank's band is ever read: fill just that
+        r0, r1 = min(t[0] for t in mine), min(S, max(t[0] + t[2] for t in mine))
+        g = torch.Generator().manual_seed(4321 + rank)
+        for ch in range(C):
+            scene[ch, r0:r1].copy_(torch.rand(r1 - r0, S, generator=g))
+    mask_host = torch.empty((S, S), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+    model._set_model_to_eval()
+    unet = model.model
+    passes, times, info = 3, [], None
+    for it in range(1 + passes):               # 1 untimed warm-up pass
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        info = predict_scene_from_host(unet, scene, crop=crop, tile_batch=args.infer_tile_batch, rank=rank,
+                                       world=world, mask_host=mask_host, device=dev)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it > 0:
+            times.append(float(t.item()))
+    model._set_model_to_train()
+    _, n_mine, launches, h2d, d2h = info
+    counts = torch.tensor([n_mine, launches, h2d], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(counts)
+    best = min(times) / 1000.0
+    peaks, _ = measured_peaks()
+    flops = len(tiles) * 320.210e9 * (crop / 512.0) ** 2 if C == 4 else None
+    water = float((mask_host != 0).float().mean()) if rank == 0 else None
+    return {"workload": f"sliding-window inference over one synthetic {S}x{S}x{C} fp32 scene in pinned host memory, "
+                        f"{len(tiles)} tiles of {crop} (stride = crop), eval-mode BatchNorm, uint8 water mask to rank 0's host",
+            "scene_seconds": best, "scene_seconds_all_passes": [x / 1000.0 for x in times],
+            "tiles_per_sec": len(tiles) / best, "n_tiles": len(tiles), "tiles_processed_all_ranks": int(counts[0]),
+            "tflops": flops / best / 1e12 if flops else None,
+            "frac_of_sustained_bf16_peak_per_gpu": (flops / best / 1e12 / world / float(peaks["bf16_tflops_sustained"]))
+                                                   if flops else None,
+            "h2d_bytes_per_scene": int(counts[2]), "d2h_bytes_per_scene": d2h, "gpu_launches_per_scene": int(counts[1]),
+            "tile_batch": args.infer_tile_batch, "water_fraction": water, "n_gpus": world}
 
 
 # ------------------------------------------------------------------------------------------
@@ -186,8 +314,14 @@ def run_ours(args):
     torch.manual_seed(0)
     model = WaterSegmentationModel({"ms_image": args.channels}, N_CLASSES, LR, ignore_index=IGNORE_INDEX).to(dev)
     broadcast_parameters(model)
-    opt = FusedAdam(model.model, lr=LR)
-    reducer = BucketedGradAllReduce(model.model) if world > 1 else None
+    if args.optimizer == "fused":
+        opt = FusedAdam(model.model, lr=LR)
+    else:                                   # the reference API's own optimiser object (water_seg_model.py:198-205)
+        opt = model.configure_optimizers()
+        opt.launches = 0
+    reducer = (BucketedGradAllReduce(model.model, transport=args.transport, max_ctas=args.nccl_max_ctas,
+                                     bucket_bytes=args.bucket_mb << 20) if world > 1 else None)
+    dp_check = data_parallel_check(model, reducer, dev, rank, world, args) if world > 1 else None
     engine = model.model._engine
     if os.environ.get("FPB200_OVERLAP_WGRAD") == "1":   # experiment switch: wgrads on a second stream
         engine.overlap_wgrad = True
@@ -227,7 +361,8 @@ def run_ours(args):
         fwd_launches = engine.launches
         loss.backward()
         opt.step()
-        launches["n"] += fwd_launches + engine.launches + 3 + 1 + opt.launches  # + CE fwd(2)/bwd(1) + where
+        # + CE fwd(2)/bwd(1) + where; torch.optim.Adam's own foreach kernels are not ours and not counted
+        launches["n"] += fwd_launches + engine.launches + 3 + 1 + opt.launches
         return loss
 
     def barrier():
@@ -372,12 +507,34 @@ def run_ours(args):
     e2e_value = B * world * args.steps / (e2e_ms / 1000.0)
     clocks = sampler.stop() if rank == 0 else None
 
+    # per-bucket timeline of the gradient all-reduce (one extra, untimed step): when each bucket became
+    # ready on the compute stream, when the collective started / ended on the communication stream
+    bucket_timeline = None
+    if reducer is not None and reducer.comm is not None:
+        reducer.timeline = []
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        train_step(pool[0], 0)
+        s1.record()
+        barrier()
+        bucket_timeline = {"step_ms": s0.elapsed_time(s1),
+                           "buckets": [{"mb": (b - a) * 4 / 1e6, "ready_ms": s0.elapsed_time(r), "start_ms": s0.elapsed_time(t0),
+                                        "end_ms": s0.elapsed_time(t1)} for a, b, r, t0, t1 in reducer.timeline]}
+        reducer.timeline = None
+
+    infer = None
+    if not args.no_infer:
+        del pool, host_pool, dev_slots
+        torch.cuda.empty_cache()
+        infer = infer_block(model, dev, rank, world, args)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        best, mean, cores, times = cpu_reference_chips_per_sec(args.cpu_sample_batch, S, 2, 1, args.channels)
+        best, mean, cores, times = cpu_reference_chips_per_sec(min(args.cpu_sample_batch, 4), S, 2, 1, args.channels)
         cpu_baseline = {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"oracle port of the reference UNet+CE+Adam train step (fp32, torch CPU), "
-                                  f"{args.cpu_sample_batch} chips of {args.channels}x{S}x{S}, 1 warm-up + best of 2 steps "
+                                  f"{min(args.cpu_sample_batch, 4)} chips of {args.channels}x{S}x{S}, 1 warm-up + best of 2 steps "
                                   f"({min(times):.2f} s/step)"}
 
     if rank == 0:
@@ -392,6 +549,12 @@ def run_ours(args):
             "cuda_graph": graphed is not None,
             "final_loss": losses[-1] if losses else None,
             "grad_buckets_per_step": reducer.buckets_last_step if reducer else 0,
+            "optimizer_impl": "fused Adam kernel over the gradient slab" if args.optimizer == "fused"
+                              else "torch.optim.Adam from configure_optimizers()",
+            "allreduce": ({"transport": reducer.transport, "max_ctas": args.nccl_max_ctas,
+                           "bucket_mb": args.bucket_mb, "timeline": bucket_timeline} if reducer else None),
+            "dp_check": dp_check,
+            "infer": infer,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -410,8 +573,20 @@ def main():
     ap.add_argument("--channels", type=int, default=4,
                     help="input bands: 4 = PlanetScope (headline); 16 = PS + S1 (2) + S2 (10) early fusion, configs[3]")
     ap.add_argument("--pool", type=int, default=2, help="distinct synthetic batches cycled through")
-    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--cpu-sample-batch", type=int, default=8,
+                    help="chips per CPU step of the reference arm / cpu_baseline leg (SURVEY 8d: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: one Adam kernel over the flat slab; torch: stock torch.optim.Adam from the "
+                         "LightningModule's configure_optimizers()")
+    ap.add_argument("--transport", default=None, choices=["capi", "torch"],
+                    help="gradient all-reduce: the C ABI's own ncclComm_t (default) or torch.distributed")
+    ap.add_argument("--nccl-max-ctas", type=int, default=int(os.environ.get("FPB200_NCCL_MAX_CTAS", "0")),
+                    help="cap of CTAs per NCCL collective for the capi transport (0 = NCCL default)")
+    ap.add_argument("--bucket-mb", type=int, default=16)
+    ap.add_argument("--no-infer", action="store_true", help="skip the configs[4] scene-inference block")
+    ap.add_argument("--infer-scene", type=int, default=10240, help="scene edge in pixels (configs[4]: 10240)")
+    ap.add_argument("--infer-tile-batch", type=int, default=50)
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step from one CUDA graph (measured: no gain at batch 64, where every "
                          "kernel is long enough to hide its launch; useful for small batches)")

@@ -20,7 +20,7 @@ LIB_PATH = LIB_DIR / "libfloodplanet_b200.so"
 INCLUDE = PKG_DIR.parent / "include"
 
 SOURCES = ["conv_igemm.cu", "conv_wgrad.cu", "elementwise.cu", "head_ce.cu", "fusion.cu",
-           "augment.cu"]
+           "augment.cu", "comm.cu"]
 
 NVCC_FLAGS = [
     "-O3",
@@ -72,7 +72,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "static", "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

@@ -62,6 +62,11 @@ SIGNATURES = {
     "fpb200_plane_mean_std_f32": (_i, [_vp, _vp, _vp, _i, _l, _vp]),
     "fpb200_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
     "fpb200_adam_step_graphable": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _vp, _f, _vp]),
+    "fpb200_nccl_version": (_i, []),
+    "fpb200_nccl_unique_id": (_i, [_vp]),
+    "fpb200_nccl_comm_create": (_i, [C.POINTER(_vp), _i, _i, _vp, _i]),
+    "fpb200_nccl_comm_destroy": (_i, [_vp]),
+    "fpb200_allreduce_f32": (_i, [_vp, _vp, _l, _i, _vp]),
 }
 
 _ERRORS = {
@@ -70,6 +75,7 @@ _ERRORS = {
     -3: "CUDA launch or runtime error",
     -4: "CUDA driver entry point unavailable",
     -5: "TMA tensor-map encode rejected the view",
+    -6: "NCCL runtime missing or NCCL call failed",
 }
 
 _LIB = None

@@ -98,3 +98,62 @@ def predict_scene(unet: UNet, scene: torch.Tensor, crop: int = 512, stride: Opti
     if distributed and not overlapping:
         torch.distributed.all_reduce(mask, op=torch.distributed.ReduceOp.MAX)
     return mask, len(mine), launches
+
+
+@torch.no_grad()
+def predict_scene_from_host(unet: UNet, scene_host: torch.Tensor, crop: int = 512, tile_batch: int = 32,
+                            rank: int = 0, world: int = 1, mask_host: Optional[torch.Tensor] = None,
+                            device: Optional[torch.device] = None):
+    """End-to-end form of :func:`predict_scene` for a scene in HOST memory -- the shape of the
+    reference loop (infer.py:112-184: `batch[key].to(device)` per batch :117-119, model, D2H :122,
+    stitch :160-163, mask :181-184), non-overlapping tiles (infer.py:64-65: stride = crop).
+
+    Each rank copies only the row band of the scene its contiguous tile range touches (host -> device,
+    one copy per channel plane; use pinned memory for an asynchronous copy), runs its tiles, stitches
+    and thresholds on the device, and the uint8 band masks are max-reduced onto rank 0, which copies
+    the full mask to `mask_host` (pinned uint8 [H, W], allocated if None).  No float logits, softmax
+    or canvas ever cross PCIe.  Returns (mask_host or None on ranks > 0, n_tiles, launches,
+    h2d_bytes, d2h_bytes)."""
+    if scene_host.is_cuda:
+        raise RuntimeError("predict_scene_from_host: the scene must be a host (ideally pinned) tensor")
+    if unet.training:
+        raise RuntimeError("predict_scene_from_host: call model.eval() first (reference: _set_model_to_eval)")
+    dev = device if device is not None else next(unet.parameters()).device
+    c, H, W = scene_host.shape
+    tiles_all = crop_slices(H, W, crop, crop, crop)
+    mine = [tiles_all[i] for i in shard_range(len(tiles_all), rank, world)]
+    engine = unet._engine
+    params = dict(unet.named_parameters())
+    buffers = dict(unet.named_buffers())
+    ncls = unet.n_classes
+    mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    launches, h2d = 0, 0
+    if mine:
+        r0 = min(t[0] for t in mine)
+        r1 = min(H, max(t[0] + t[2] for t in mine))
+        band = torch.empty((c, r1 - r0, W), dtype=torch.float32, device=dev)
+        for ch in range(c):                                   # each plane slice is contiguous on the host
+            band[ch].copy_(scene_host[ch, r0:r1], non_blocking=True)
+        h2d = band.numel() * 4
+        canvas = torch.zeros((r1 - r0, W, ncls), dtype=torch.float32, device=dev)
+        weight = torch.zeros((r1 - r0, W), dtype=torch.float32, device=dev)
+        for b0 in range(0, len(mine), tile_batch):
+            chunk = mine[b0:b0 + tile_batch]
+            meta = [[h0 - r0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
+            tdev = torch.tensor(meta, dtype=torch.int32, device=dev)
+            x = ops.ingest_scene_tiles(band, tdev, crop, crop, engine.cin_pad)
+            logits, _ = engine.forward(None, params, buffers, training=False, save=False, ingested=x)
+            ops.softmax_stitch_add(logits, canvas, weight, tdev)
+            launches += engine.launches + 2
+        # pixels of the band no tile of THIS rank covers keep weight 0 -> canvas 0 -> argmax 0 -> mask 0
+        ops.canvas_to_mask_u8(canvas, weight, mask[r0:r1])
+        launches += 1
+    if world > 1 and torch.distributed.is_initialized():
+        torch.distributed.reduce(mask, dst=0, op=torch.distributed.ReduceOp.MAX)
+    d2h = 0
+    out = None
+    if rank == 0:
+        out = mask_host if mask_host is not None else torch.empty((H, W), dtype=torch.uint8, pin_memory=True)
+        out.copy_(mask, non_blocking=False)                   # device -> host, synchronises
+        d2h = mask.numel()
+    return out, len(mine), launches, h2d, d2h

@@ -32,6 +32,7 @@ extern "C" {
 #define FPB200_ERR_LAUNCH (-3)    /* CUDA launch / runtime error (message on stderr)  */
 #define FPB200_ERR_DRIVER (-4)    /* driver entry point unavailable (no GPU driver)   */
 #define FPB200_ERR_TENSORMAP (-5) /* cuTensorMapEncodeTiled rejected the view         */
+#define FPB200_ERR_NCCL (-6)      /* NCCL runtime missing, or an NCCL call failed     */
 
 /* library identification: returns the ABI version (bumped on any signature change). */
 int fpb200_abi_version(void);
@@ -331,6 +332,30 @@ int fpb200_adam_step(float* p, const float* g, float* m, float* v, long n, float
 int fpb200_adam_step_graphable(float* p, const float* g, float* m, float* v, long n, float lr,
                                float beta1, float beta2, float eps, int* step_state,
                                float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel exchange step: gradient all-reduce over an ncclComm_t.
+ * NEW capability -- the reference trains on one GPU (fit.py:86-88 `devices=1`); the call these
+ * replace is what torch-DDP would add around `loss.backward()` (water_seg_model.py:98-136).
+ * NCCL is resolved at RUN time from the libnccl.so.2 already loaded in the process (the one
+ * torch bundles) or else from the system library; the library has no link-time dependency on it
+ * and loads on a box without NCCL (fpb200_nccl_version() then returns 0).
+ * ---------------------------------------------------------------------------------------- */
+#define FPB200_NCCL_UNIQUE_ID_BYTES 128
+
+/* NCCL_VERSION_CODE of the runtime that was found (e.g. 22809), 0 if none. */
+int fpb200_nccl_version(void);
+/* Rank 0: a fresh ncclUniqueId (128 bytes) to hand to every rank out of band (torch.distributed
+ * store, MPI, a file ...). */
+int fpb200_nccl_unique_id(void* id128);
+/* Every rank: *comm = ncclCommInitRankConfig(world, id, rank) on the CURRENT device.  max_ctas > 0
+ * caps the CTAs (= SMs) one collective may occupy (ncclConfig_t.maxCTAs): the all-reduce overlaps
+ * persistent one-CTA-per-SM convolution kernels, every SM it takes delays a conv wave; 0 = NCCL default. */
+int fpb200_nccl_comm_create(void** comm, int world, int rank, const void* id128, int max_ctas);
+int fpb200_nccl_comm_destroy(void* comm);
+/* In-place all-reduce of `count` fp32 values at `buf` on `stream`: average (op_avg = 1, ncclAvg: the
+ * 1/world scaling happens inside the collective) or sum (op_avg = 0).  Asynchronous w.r.t. the host. */
+int fpb200_allreduce_f32(void* comm, float* buf, long count, int op_avg, void* stream);
 
 #ifdef __cplusplus
 }

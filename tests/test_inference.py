@@ -100,3 +100,27 @@ def test_device_stitch_kernels_match_reference_stitcher_golden():
             assert np.array_equal(got, want)
         else:
             assert (got != want).mean() < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,crop", [(96, 64, 32), (100, 70, 32)])
+def test_predict_scene_from_host_equals_device_resident_path(H, W, crop):
+    """The end-to-end form (scene in pinned host memory, per-rank row band H2D, uint8 mask D2H; the shape of
+    infer.py:112-184) gives bit-identical masks to the device-resident path, also when tile-sharded."""
+    from floodplanet_code_b200.inference import predict_scene, predict_scene_from_host
+    m = _model()
+    scene = torch.rand(4, H, W, generator=torch.Generator().manual_seed(8))
+    want, n, _ = predict_scene(m, scene.cuda(), crop=crop, stride=crop, tile_batch=5)
+    host = scene.pin_memory()
+    got, n1, launches, h2d, d2h = predict_scene_from_host(m, host, crop=crop, tile_batch=5)
+    assert n1 == n and launches > 0 and h2d == scene.numel() * 4 and d2h == H * W
+    assert got.dtype == torch.uint8 and not got.is_cuda and torch.equal(got, want.cpu())
+    # each rank of a 3-way shard copies only its row band
+    from floodplanet_code_b200.inference import crop_slices
+    from floodplanet_code_b200.parallel import shard_range
+    tiles_all = crop_slices(H, W, crop, crop, crop)
+    for r in range(3):
+        mine = [tiles_all[i] for i in shard_range(len(tiles_all), r, 3)]
+        rows = min(H, max(t[0] + t[2] for t in mine)) - min(t[0] for t in mine)
+        _, k, _, hb, _ = predict_scene_from_host(m, host, crop=crop, tile_batch=4, rank=r, world=3)
+        assert k == len(mine) and hb == 4 * rows * W * 4

@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, transport):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     import torch.distributed as dist
@@ -31,29 +31,37 @@ def _worker(rank, world, port, q):
     m.model.load_state_dict(O.init_state_dict(4, 3, seed=0))
     m = m.cuda()
     broadcast_parameters(m)
-    BucketedGradAllReduce(m.model, bucket_bytes=1 << 20)
+    red = BucketedGradAllReduce(m.model, bucket_bytes=1 << 20, transport=transport, max_ctas=8 if transport == "capi" else 0)
+    assert red.transport == transport and (red.comm is not None) == (transport == "capi")
     b = O.synthetic_batch(2, 4, 64, 64, seed=10 + rank, block=8, device="cuda")
     loss = m.training_step(b, 0)
     loss.backward()
     torch.cuda.synchronize()
     g = {k: p.grad.detach().cpu() for k, p in m.model.named_parameters()}
-    q.put((rank, g))
+    q.put((rank, g, red.buckets_last_step))
     dist.barrier()
+    if red.comm is not None:
+        red.comm.destroy()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_allreduce_equals_mean_of_shard_gradients():
+@pytest.mark.parametrize("transport", ["capi", "torch"])
+def test_two_gpu_allreduce_equals_mean_of_shard_gradients(transport):
+    """transport 'capi': the C ABI's own ncclComm_t (fpb200_nccl_comm_create / fpb200_allreduce_f32, ncclAvg)
+    on the module's communication stream; 'torch': torch.distributed all_reduce(AVG)."""
     from floodplanet_code_b200.water_seg_model import WaterSegmentationModel
     from oracle import unet_oracle as O
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, transport)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in range(world))
+    got = [q.get(timeout=300) for _ in range(world)]
+    res = {r: g for r, g, _ in got}
+    assert all(nb >= 4 for _, _, nb in got), "the 69 MB slab should leave in several buckets during backward"
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

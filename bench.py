@@ -319,9 +319,12 @@ def run_ours(args):
     else:                                   # the reference API's own optimiser object (water_seg_model.py:198-205)
         opt = model.configure_optimizers()
         opt.launches = 0
+    # --no-allreduce: N independent replicas (no exchange step) -- NOT data-parallel training, only a probe
+    # that separates GPU-to-GPU speed variance (max over ranks) from the cost of the collective
     reducer = (BucketedGradAllReduce(model.model, transport=args.transport, max_ctas=args.nccl_max_ctas,
-                                     bucket_bytes=args.bucket_mb << 20) if world > 1 else None)
-    dp_check = data_parallel_check(model, reducer, dev, rank, world, args) if world > 1 else None
+                                     bucket_bytes=args.bucket_mb << 20)
+               if world > 1 and not args.no_allreduce else None)
+    dp_check = data_parallel_check(model, reducer, dev, rank, world, args) if reducer is not None else None
     engine = model.model._engine
     if os.environ.get("FPB200_OVERLAP_WGRAD") == "1":   # experiment switch: wgrads on a second stream
         engine.overlap_wgrad = True
@@ -388,7 +391,11 @@ def run_ours(args):
     elapsed_ms = e0.elapsed_time(e1)
     gpu_launches = launches["n"]
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    per_rank_ms = None
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(x.item()) / args.steps for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
@@ -554,6 +561,9 @@ def run_ours(args):
             "allreduce": ({"transport": reducer.transport, "max_ctas": args.nccl_max_ctas,
                            "bucket_mb": args.bucket_mb, "timeline": bucket_timeline} if reducer else None),
             "dp_check": dp_check,
+            "per_rank_ms_per_step": per_rank_ms,
+            "exchange_step": ("none (independent replicas: probe only)" if world > 1 and reducer is None
+                              else ("gradient all-reduce" if world > 1 else None)),
             "infer": infer,
         }
         print(json.dumps(line), flush=True)
@@ -584,6 +594,8 @@ def main():
     ap.add_argument("--nccl-max-ctas", type=int, default=int(os.environ.get("FPB200_NCCL_MAX_CTAS", "0")),
                     help="cap of CTAs per NCCL collective for the capi transport (0 = NCCL default)")
     ap.add_argument("--bucket-mb", type=int, default=16)
+    ap.add_argument("--no-allreduce", action="store_true",
+                    help="probe: N independent replicas without the gradient exchange (not a training configuration)")
     ap.add_argument("--no-infer", action="store_true", help="skip the configs[4] scene-inference block")
     ap.add_argument("--infer-scene", type=int, default=10240, help="scene edge in pixels (configs[4]: 10240)")
     ap.add_argument("--infer-tile-batch", type=int, default=50)

@@ -100,6 +100,16 @@ def predict_scene(unet: UNet, scene: torch.Tensor, crop: int = 512, stride: Opti
     return mask, len(mine), launches
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
 @torch.no_grad()
 def predict_scene_from_host(unet: UNet, scene_host: torch.Tensor, crop: int = 512, tile_batch: int = 32,
                             rank: int = 0, world: int = 1, mask_host: Optional[torch.Tensor] = None,
@@ -108,8 +118,10 @@ def predict_scene_from_host(unet: UNet, scene_host: torch.Tensor, crop: int = 51
     reference loop (infer.py:112-184: `batch[key].to(device)` per batch :117-119, model, D2H :122,
     stitch :160-163, mask :181-184), non-overlapping tiles (infer.py:64-65: stride = crop).
 
-    Each rank copies only the row band of the scene its contiguous tile range touches (host -> device,
-    one copy per channel plane; use pinned memory for an asynchronous copy), runs its tiles, stitches
+    Each rank copies only the rows of the scene its contiguous tile range touches (host -> device, one
+    tile batch at a time on a copy stream that runs one batch ahead of the compute stream; use pinned
+    memory, and a `tile_batch` that is a multiple of the tiles per scene row so no row is copied twice),
+    runs its tiles, stitches
     and thresholds on the device, and the uint8 band masks are max-reduced onto rank 0, which copies
     the full mask to `mask_host` (pinned uint8 [H, W], allocated if None).  No float logits, softmax
     or canvas ever cross PCIe.  Returns (mask_host or None on ranks > 0, n_tiles, launches,
@@ -131,20 +143,54 @@ def predict_scene_from_host(unet: UNet, scene_host: torch.Tensor, crop: int = 51
     if mine:
         r0 = min(t[0] for t in mine)
         r1 = min(H, max(t[0] + t[2] for t in mine))
-        band = torch.empty((c, r1 - r0, W), dtype=torch.float32, device=dev)
-        for ch in range(c):                                   # each plane slice is contiguous on the host
-            band[ch].copy_(scene_host[ch, r0:r1], non_blocking=True)
-        h2d = band.numel() * 4
         canvas = torch.zeros((r1 - r0, W, ncls), dtype=torch.float32, device=dev)
         weight = torch.zeros((r1 - r0, W), dtype=torch.float32, device=dev)
-        for b0 in range(0, len(mine), tile_batch):
-            chunk = mine[b0:b0 + tile_batch]
-            meta = [[h0 - r0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
-            tdev = torch.tensor(meta, dtype=torch.int32, device=dev)
-            x = ops.ingest_scene_tiles(band, tdev, crop, crop, engine.cin_pad)
+        # host -> device copies run on their own stream, one tile batch ahead of the compute stream
+        # (two row-band buffers, events both ways), so PCIe time hides behind the UNet of the previous batch
+        batches = [mine[b0:b0 + tile_batch] for b0 in range(0, len(mine), tile_batch)]
+        spans = [(min(t[0] for t in ch), min(H, max(t[0] + t[2] for t in ch))) for ch in batches]
+        max_rows = max(e - s0 for s0, e in spans)
+        bufs = [torch.empty((c, max_rows, W), dtype=torch.float32, device=dev) for _ in range(min(2, len(batches)))]
+        compute = torch.cuda.current_stream(dev)
+        copier = _copy_stream(dev)
+        ready = [torch.cuda.Event() for _ in bufs]
+        consumed = [torch.cuda.Event() for _ in bufs]
+        for ev in consumed:
+            ev.record(compute)
+
+        def band_view(i):
+            """Dense [C, rows_i, W] view of slot i % 2 (the ingest kernel addresses a contiguous scene)."""
+            s0, e = spans[i]
+            return bufs[i % len(bufs)].view(-1)[:c * (e - s0) * W].view(c, e - s0, W)
+
+        def stage(i):
+            s0, e = spans[i]
+            slot = i % len(bufs)
+            band = band_view(i)
+            with torch.cuda.stream(copier):
+                copier.wait_event(consumed[slot])
+                for ch in range(c):                           # each plane slice is contiguous on the host
+                    band[ch].copy_(scene_host[ch, s0:e], non_blocking=True)
+                ready[slot].record(copier)
+            return c * (e - s0) * W * 4
+
+        h2d += stage(0)
+        for i, chunk in enumerate(batches):
+            if i + 1 < len(batches):
+                h2d += stage(i + 1)
+            slot = i % len(bufs)
+            s0, e = spans[i]
+            compute.wait_event(ready[slot])
+            meta_in = [[h0 - s0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
+            x = ops.ingest_scene_tiles(band_view(i), torch.tensor(meta_in, dtype=torch.int32, device=dev),
+                                       crop, crop, engine.cin_pad)
+            consumed[slot].record(compute)                    # the band buffer may be overwritten from here on
             logits, _ = engine.forward(None, params, buffers, training=False, save=False, ingested=x)
-            ops.softmax_stitch_add(logits, canvas, weight, tdev)
+            meta_out = [[h0 - r0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
+            ops.softmax_stitch_add(logits, canvas, weight, torch.tensor(meta_out, dtype=torch.int32, device=dev))
             launches += engine.launches + 2
+        for buf in bufs:
+            buf.record_stream(copier)
         # pixels of the band no tile of THIS rank covers keep weight 0 -> canvas 0 -> argmax 0 -> mask 0
         ops.canvas_to_mask_u8(canvas, weight, mask[r0:r1])
         launches += 1

@@ -113,14 +113,21 @@ def test_predict_scene_from_host_equals_device_resident_path(H, W, crop):
     want, n, _ = predict_scene(m, scene.cuda(), crop=crop, stride=crop, tile_batch=5)
     host = scene.pin_memory()
     got, n1, launches, h2d, d2h = predict_scene_from_host(m, host, crop=crop, tile_batch=5)
-    assert n1 == n and launches > 0 and h2d == scene.numel() * 4 and d2h == H * W
+    # (a batch that starts inside a tile row re-copies that row band: >=; equality for aligned batches below)
+    assert n1 == n and launches > 0 and h2d >= scene.numel() * 4 and d2h == H * W
     assert got.dtype == torch.uint8 and not got.is_cuda and torch.equal(got, want.cpu())
-    # each rank of a 3-way shard copies only its row band
+    # batches aligned to whole tile rows copy every scene row exactly once, and several batches (two band
+    # buffers, copy stream one batch ahead) give the same mask as one
+    if H % crop == 0 and W % crop == 0:
+        per_row = W // crop
+        got2, _, _, h2d2, _ = predict_scene_from_host(m, host, crop=crop, tile_batch=per_row)
+        assert h2d2 == scene.numel() * 4 and torch.equal(got2, got)
+    # each rank of a 3-way shard copies only the rows its tiles touch
     from floodplanet_code_b200.inference import crop_slices
     from floodplanet_code_b200.parallel import shard_range
     tiles_all = crop_slices(H, W, crop, crop, crop)
     for r in range(3):
         mine = [tiles_all[i] for i in shard_range(len(tiles_all), r, 3)]
         rows = min(H, max(t[0] + t[2] for t in mine)) - min(t[0] for t in mine)
-        _, k, _, hb, _ = predict_scene_from_host(m, host, crop=crop, tile_batch=4, rank=r, world=3)
+        _, k, _, hb, _ = predict_scene_from_host(m, host, crop=crop, tile_batch=64, rank=r, world=3)
         assert k == len(mine) and hb == 4 * rows * W * 4

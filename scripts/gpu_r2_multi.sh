@@ -18,7 +18,6 @@ if [ "$N" != "2" ]; then
   python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-infer > gpurun_out/r2m_n${N}_samebox_n1.json 2> gpurun_out/r2m_n${N}_samebox_n1.err
   run torch --transport torch --no-infer
   run capi_cta8 --nccl-max-ctas 8 --no-infer
-  run capi_cta16 --nccl-max-ctas 16 --no-infer
   run capi_onebucket --bucket-mb 128 --no-infer
   run replicas --no-allreduce --no-infer
 fi

@@ -131,3 +131,43 @@ def test_predict_scene_from_host_equals_device_resident_path(H, W, crop):
         rows = min(H, max(t[0] + t[2] for t in mine)) - min(t[0] for t in mine)
         _, k, _, hb, _ = predict_scene_from_host(m, host, crop=crop, tile_batch=64, rank=r, world=3)
         assert k == len(mine) and hb == 4 * rows * W * 4
+
+
+@pytest.mark.gpu
+def test_infer_py_shaped_loop_through_the_model_registry():
+    """The caller's side of the seam, written the way the reference's infer.py:86-184 drives it: build_model
+    by registry name, `_set_model_to_eval()`, `.to('cuda')`, per batch `batch[key].to(device)`,
+    `model(batch).detach().cpu().numpy()` (fp32 logits for numpy), scipy softmax, `b c h w -> b h w c`,
+    ImageStitcher-style accumulation (the pinned oracle Stitcher), `np.clip(argmax, 0, 1) * 255`.  The mask
+    must equal the tile-sharded device path's."""
+    from scipy.special import softmax
+    from floodplanet_code_b200.inference import crop_slices, predict_scene
+    from floodplanet_code_b200.water_seg_model import build_model
+    H, W, crop = 96, 128, 32
+    model = build_model("ef_model", {"ms_image": 4, "dem": 1}, 3, 1e-4, 50, None, 0)
+    model.model.load_state_dict(O.init_state_dict(5, 3, seed=2))
+    model._set_model_to_eval()
+    model = model.to("cuda")
+    device = "cuda"
+    g = torch.Generator().manual_seed(11)
+    scene = torch.rand(5, H, W, generator=g)
+    tiles = crop_slices(H, W, crop, crop, crop)
+    st = T.Stitcher(H, W, 3)
+    with torch.no_grad():
+        for b0 in range(0, len(tiles), 5):                       # DataLoader batches of crops + metadata
+            chunk = tiles[b0:b0 + 5]
+            batch = {"image": torch.stack([scene[:4, h0:h0 + hh, w0:w0 + ww] for h0, w0, hh, ww in chunk]),
+                     "dem": torch.stack([scene[4:5, h0:h0 + hh, w0:w0 + ww] for h0, w0, hh, ww in chunk]),
+                     "metadata": [{"crop_params": t} for t in chunk]}
+            for key, value in batch.items():
+                if isinstance(value, torch.Tensor):
+                    batch[key] = value.to(device)
+            output = model(batch).detach().cpu().numpy()
+            assert output.dtype == np.float32 and output.shape == (len(chunk), 3, crop, crop)
+            preds = softmax(output, axis=1).transpose(0, 2, 3, 1)
+            for b, (h0, w0, hh, ww) in enumerate(chunk):
+                st.add(preds[b], h0, w0, hh, ww)
+    want = (np.clip(st.combined().argmax(axis=2), 0, 1) * 255).astype("uint8")
+    # the device path: same UNet object, early-fusion channels pre-concatenated in the scene
+    got, n, _ = predict_scene(model.model, scene.cuda(), crop=crop, stride=crop, tile_batch=7)
+    assert n == len(tiles) and np.array_equal(got.cpu().numpy(), want)

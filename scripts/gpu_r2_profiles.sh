@@ -2,6 +2,10 @@
 # round 2 evidence (1 GPU): launch list of one training step, ncu --set full of the CURRENT conv kernel modes,
 # cuDNN / torch.compile yardstick.  Every ncu command runs only after the same command exited 0 without ncu.
 mkdir -p gpurun_out
+# tcgen05 operand-path microbenchmark (built on the box: gpurun_out/ does not travel)
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I floodplanet_code_b200/csrc scripts/umma_microbench.cu \
+    -o gpurun_out/umma_microbench > gpurun_out/r2p_umma_build.log 2>&1 && timeout 120 gpurun_out/umma_microbench > gpurun_out/r2p_umma_microbench.txt 2>&1
+echo "umma microbench rc=$?"; cat gpurun_out/r2p_umma_microbench.txt
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-infer"
 timeout 600 $B > gpurun_out/r2p_plain.log 2>&1 &&
 timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \

@@ -441,13 +441,14 @@ def run_ours(args):
     conv_flops = sum(d["flops"] for d in fam.values())
     dom = max(fam.items(), key=lambda kv: kv[1]["ms"])[0] if fam else None
     traffic, traffic_src = None, None
-    tp = ROOT / "profiles" / "r01_traffic.json"
+    cands = sorted((ROOT / "profiles").glob("r*_traffic.json"))
+    tp = cands[-1] if cands else ROOT / "profiles" / "r01_traffic.json"      # the latest round's capture
     if tp.exists() and dom is not None:
         tj = json.loads(tp.read_text())
         key = "conv3x3_wgrad_kernel_all" if dom == "wgrad" else "conv3x3_halo_kernel_all"
         traffic = tj[key]["dram_bytes_per_launch"]
         traffic_src = ("mean dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel over one "
-                       "training step at batch 64 (profiles/r01_traffic.json, ncu)")
+                       f"training step at batch 64 (profiles/{tp.name}, ncu)")
     roofline = None
     if dom is not None:
         kname = {"fprop": "conv3x3_halo_kernel (fprop launches)", "dgrad": "conv3x3_halo_kernel (dgrad launches)",

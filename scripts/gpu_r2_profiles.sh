@@ -17,8 +17,9 @@ timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"co
     -c 24 -o gpurun_out/r2p_conv_modes $M > gpurun_out/r2p_ncu_modes.log 2>&1
 echo "ncu modes rc=$?"
 ncu -i gpurun_out/r2p_conv_modes.ncu-rep --page raw --csv > gpurun_out/r2p_conv_modes_raw.csv 2>/dev/null
+rm -f gpurun_out/r2p_conv_modes.ncu-rep      # 77 MB: gpurun merges back at most 64 MiB; the raw CSV carries every metric
 python scripts/conv_microbench.py --batch 64 > gpurun_out/r2p_conv_microbench_b64.txt 2>&1
-timeout 1500 python scripts/yardstick_cudnn.py --batch 64 --steps 5 --compile-timeout 700 --out gpurun_out/r2p_yardstick.json \
+[ "$SKIP_YARDSTICK" = "1" ] || timeout 1500 python scripts/yardstick_cudnn.py --batch 64 --steps 5 --compile-timeout 700 --out gpurun_out/r2p_yardstick.json \
     > gpurun_out/r2p_yardstick.log 2>&1
 echo "yardstick rc=$?"; tail -n 4 gpurun_out/r2p_yardstick.log | cut -c1-300
 tail -n 3 gpurun_out/r2p_conv_microbench_b64.txt

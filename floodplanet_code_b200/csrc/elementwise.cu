@@ -51,10 +51,11 @@ static inline int grid_for(long work, int block, int max_blocks) {
 // ---------------------------------------------------------------------------
 // ingest: NCHW f32 (x n_src, concatenated along C) -> NHWC bf16, C zero-padded
 // ---------------------------------------------------------------------------
+constexpr int kIngestMaxC = 256;   // padded input channels of the first convolution (early fusion of many sensors)
 struct IngestArgs {
   const float* src[8];
-  unsigned char ch_src[64];  // for padded channel c: which source
-  unsigned char ch_idx[64];  // ... and which channel inside it (255 = zero pad)
+  unsigned char ch_src[kIngestMaxC];  // for padded channel c: which source
+  unsigned char ch_idx[kIngestMaxC];  // ... and which channel inside it (255 = zero pad)
   int src_c[8];
 };
 
@@ -965,7 +966,9 @@ int fpb200_abi_version(void) { return 1; }
 int fpb200_ingest_nchw_f32_to_nhwc_bf16(const float* const* srcs, const int* src_channels,
                                         int n_src, void* dst, int c_pad, int N, int H, int W,
                                         void* stream) {
-  if (n_src < 1 || n_src > 8 || c_pad % 8 != 0 || c_pad > 64) return FPB200_ERR_SHAPE;
+  if (n_src < 1 || n_src > 8 || c_pad % 8 != 0 || c_pad > kIngestMaxC) return FPB200_ERR_SHAPE;
+  for (int s = 0; s < n_src; ++s)
+    if (src_channels[s] < 1 || src_channels[s] > 255) return FPB200_ERR_SHAPE;   // 255 is the zero-pad marker
   IngestArgs a;
   int c = 0;
   for (int s = 0; s < 8; ++s) { a.src[s] = nullptr; a.src_c[s] = 0; }
@@ -979,7 +982,7 @@ int fpb200_ingest_nchw_f32_to_nhwc_bf16(const float* const* srcs, const int* src
       ++c;
     }
   }
-  for (; c < 64; ++c) { a.ch_src[c] = 0; a.ch_idx[c] = 255; }
+  for (; c < kIngestMaxC; ++c) { a.ch_src[c] = 0; a.ch_idx[c] = 255; }
   const long total = (long)N * H * W;
   ingest_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       a, (__nv_bfloat16*)dst, c_pad, N, (long)H * W);
@@ -988,7 +991,7 @@ int fpb200_ingest_nchw_f32_to_nhwc_bf16(const float* const* srcs, const int* src
 
 int fpb200_ingest_scene_tiles(const float* scene, int C, long H, long W, const int* tiles,
                               int n_tiles, int th, int tw, void* dst, int c_pad, void* stream) {
-  if (c_pad % 8 != 0 || c_pad > 64 || C > c_pad || n_tiles < 1) return FPB200_ERR_SHAPE;
+  if (c_pad % 8 != 0 || c_pad > kIngestMaxC || C > c_pad || n_tiles < 1) return FPB200_ERR_SHAPE;
   const long total = (long)n_tiles * th * tw;
   ingest_scene_tiles_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       scene, C, H, W, tiles, n_tiles, th, tw, (__nv_bfloat16*)dst, c_pad);

@@ -28,6 +28,7 @@ from . import ops
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+MAX_INPUT_CHANNELS = 256     # after early fusion, padded (csrc/elementwise.cu: kIngestMaxC)
 
 
 def pad_channels(c: int) -> int:
@@ -647,8 +648,8 @@ class UNetEngine(_Schedule):
         self.n_channels = n_channels
         self.n_classes = n_classes
         self.cin_pad = pad_channels(n_channels)
-        if self.cin_pad > 64:
-            raise RuntimeError(f"floodplanet_b200: {n_channels} input channels unsupported (max 64)")
+        if self.cin_pad > MAX_INPUT_CHANNELS:
+            raise RuntimeError(f"floodplanet_b200: {n_channels} input channels unsupported (max {MAX_INPUT_CHANNELS})")
         self.enc_specs = encoder_conv_specs(n_channels)
         self.dec_specs = decoder_conv_specs()
         self.specs = self.enc_specs + self.dec_specs
@@ -728,8 +729,8 @@ class EncoderEngine(_Schedule):
         super().__init__()
         self.n_channels = n_channels
         self.cin_pad = pad_channels(n_channels)
-        if self.cin_pad > 64:
-            raise RuntimeError(f"floodplanet_b200: {n_channels} input channels unsupported (max 64)")
+        if self.cin_pad > MAX_INPUT_CHANNELS:
+            raise RuntimeError(f"floodplanet_b200: {n_channels} input channels unsupported (max {MAX_INPUT_CHANNELS})")
         self.specs = encoder_conv_specs(n_channels, prefix)
         _number(self.specs)
         self.names = conv_param_names(self.specs)
@@ -830,8 +831,8 @@ class LateFusionEngine(_Schedule):
         k = 0
         for name, c in in_channels.items():
             self.cin_pad[name] = pad_channels(c)
-            if self.cin_pad[name] > 64:
-                raise RuntimeError(f"floodplanet_b200: {c} input channels unsupported (max 64)")
+            if self.cin_pad[name] > MAX_INPUT_CHANNELS:
+                raise RuntimeError(f"floodplanet_b200: {c} input channels unsupported (max {MAX_INPUT_CHANNELS})")
             self.enc_specs[name] = encoder_conv_specs(c, f"encoders.{name}.")
             _number(self.enc_specs[name], k)
             k += len(self.enc_specs[name])

@@ -264,6 +264,35 @@ def test_early_fusion_model_matches_concat():
     assert rel(out, fx["logits_train"]) < NET_LOGIT_ENVELOPE
 
 
+def test_wide_early_fusion_input_beyond_64_channels():
+    """More than 64 input bands (PlanetScope + Sentinel-1/2 + Landsat-8 + terrain stacks): the first
+    convolution runs with two 64-channel K chunks; teacher-forced walk + loss against the fp32 oracle."""
+    from floodplanet_code_b200.loss import MaskedCrossEntropyLoss
+    from floodplanet_code_b200.unet import UNet
+    from oracle import teacher_forced as TF
+    c_in = 70
+    sd = O.init_state_dict(c_in, 3, seed=4)
+    m = UNet(c_in, 3)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    b = O.synthetic_batch(2, c_in, 48, 64, seed=6, block=8, device="cuda")
+    m._engine.trace = []
+    logits = m(b["image"])
+    loss = MaskedCrossEntropyLoss(0)(logits, b["target"])
+    loss.backward()
+    torch.cuda.synchronize()
+    trace, m._engine.trace = m._engine.trace, None
+    assert trace[0]["x"].shape[3] == 128                         # padded to two 64-channel chunks
+    report = TF.walk(m, {k: v.cuda() for k, v in sd.items()}, b, logits.detach(), loss.detach(), trace, 0,
+                     fwd_tol=5e-3, grad_tol=5e-3)
+    assert len(report) >= 140
+    oloss, _, ologits, _ = O.training_step({k: v.cuda() for k, v in sd.items()}, b, 0, early_fusion=False)
+    assert abs(float(loss) - float(oloss)) <= LOGIT_TOL * abs(float(oloss))
+    assert rel(logits, ologits) < NET_LOGIT_ENVELOPE
+    with pytest.raises(RuntimeError):
+        UNet(300, 3)
+
+
 def test_cpu_input_raises_no_fallback():
     from floodplanet_code_b200.unet import UNet
     m = UNet(4, 3)

@@ -384,19 +384,40 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    marks = []
     for i in range(args.steps):
         train_step(pool[i % len(pool)], i)
+        if world > 1:                       # per-step boundaries (no host sync): step-time jitter across ranks
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
     gpu_launches = launches["n"]
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     per_rank_ms = None
+    step_jitter = None
     if world > 1:
         every = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(every, t)
         per_rank_ms = [float(x.item()) / args.steps for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # per-step durations of every rank: what a per-step synchronisation to the slowest rank costs
+        # (mean over steps of the max over ranks) against the max over ranks of the per-rank means
+        prev, mine = e0, []
+        for ev in marks:
+            mine.append(prev.elapsed_time(ev))
+            prev = ev
+        st = torch.tensor(mine, device=dev, dtype=torch.float64)
+        allst = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(allst, st)
+        allst = torch.stack(allst).cpu()                       # [rank, step]
+        step_jitter = {"mean_over_steps_of_max_over_ranks_ms": float(allst.max(0).values.mean()),
+                       "max_over_ranks_of_mean_over_steps_ms": float(allst.mean(1).max()),
+                       "per_rank_step_std_ms": [float(x) for x in allst.std(1)],
+                       "per_rank_min_step_ms": [float(x) for x in allst.min(1).values],
+                       "per_rank_max_step_ms": [float(x) for x in allst.max(1).values]}
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = B * world * args.steps / (elapsed_ms / 1000.0)
@@ -563,6 +584,7 @@ def run_ours(args):
                            "bucket_mb": args.bucket_mb, "timeline": bucket_timeline} if reducer else None),
             "dp_check": dp_check,
             "per_rank_ms_per_step": per_rank_ms,
+            "step_jitter": step_jitter,
             "exchange_step": ("none (independent replicas: probe only)" if world > 1 and reducer is None
                               else ("gradient all-reduce" if world > 1 else None)),
             "infer": infer,

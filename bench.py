@@ -621,7 +621,7 @@ def main():
                     help="probe: N independent replicas without the gradient exchange (not a training configuration)")
     ap.add_argument("--no-infer", action="store_true", help="skip the configs[4] scene-inference block")
     ap.add_argument("--infer-scene", type=int, default=10240, help="scene edge in pixels (configs[4]: 10240)")
-    ap.add_argument("--infer-tile-batch", type=int, default=40,
+    ap.add_argument("--infer-tile-batch", type=int, default=20,
                     help="tiles per forward; a multiple of the tiles per scene row (20) copies no row twice")
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step from one CUDA graph (measured: no gain at batch 64, where every "

@@ -152,7 +152,7 @@ class UNet(nn.Module):
         # eval mode (or no_grad): forward only.  Backward through running-statistics BatchNorm is not
         # built (no caller in the reference differentiates an eval-mode forward: validation / infer /
         # predict all run under no_grad); the logits carry no graph, so a `.backward()` on them fails
-        # loudly in torch rather than training nothing.  See INTEGRATION.md "Limits".
+        # loudly in torch rather than training nothing.  See INTEGRATION.md section 7 "Limits".
         with torch.no_grad():
             logits, _ = engine.forward(images, params, dict(self.named_buffers()),
                                        training=self.training, save=False)

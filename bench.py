@@ -592,6 +592,8 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if reducer is not None and reducer.comm is not None:
+            reducer.comm.destroy()
         dist.destroy_process_group()
 
 

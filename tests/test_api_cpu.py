@@ -189,3 +189,24 @@ def test_repack_batch_table_layout():
     recs = [struct.unpack_from("<QQiiiiq", bytes(table.numpy().tobytes()), 40 * i) for i in range(2)]
     assert recs[0] == (w1.data_ptr(), o1.data_ptr(), 8, 4, 16, 0, 0)
     assert recs[1] == (w2.data_ptr(), o2.data_ptr(), 16, 8, 8, 1, 8)
+
+
+def test_nccl_entry_points_validate_arguments_without_a_gpu():
+    """The exchange-step entry points bind NCCL at run time (dlopen of the libnccl.so.2 torch already loaded);
+    argument errors come back as status codes, nothing needs a device until a communicator is created."""
+    import ctypes as C
+    from floodplanet_code_b200 import capi
+    lib = capi.load()
+    ver = lib.fpb200_nccl_version()
+    assert ver == 0 or ver >= 21800                       # 0 = no NCCL runtime in this process
+    ident = (C.c_char * 128)()
+    handle = C.c_void_p()
+    if ver:
+        assert lib.fpb200_nccl_unique_id(ident) == 0 and any(bytes(ident))
+        assert lib.fpb200_nccl_comm_create(C.byref(handle), 2, 5, ident, 0) == -1      # rank outside [0, world)
+        assert lib.fpb200_nccl_comm_create(C.byref(handle), 0, 0, ident, 0) == -1
+    assert lib.fpb200_nccl_unique_id(None) == -6
+    assert lib.fpb200_allreduce_f32(None, None, 16, 1, None) == -6                     # no communicator
+    assert lib.fpb200_nccl_comm_destroy(None) == -6
+    with pytest.raises(RuntimeError, match="NCCL"):
+        capi.check(-6, "allreduce_f32", count=16)

@@ -31,6 +31,8 @@ SIGNATURES = {
     "fpb200_conv3x3_wgrad_bf16_nhwc": (_i, [_vp, _l, _vp, _l, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fpb200_bn_stats_finalize": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fpb200_bn_fold_eval": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    "fpb200_bn_eval_stats": (_i, [_vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    "fpb200_bn_bwd_finalize_frozen": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fpb200_bn_apply_relu": (_i, [_vp, _l, _vp, _l, _vp, _vp, _l, _i, _vp]),
     "fpb200_bn_apply_relu_maxpool2": (_i, [_vp, _l, _vp, _l, _vp, _l, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fpb200_maxpool2_bwd": (_i, [_vp, _l, _vp, _vp, _l, _vp, _l, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp, _vp, _vp,

@@ -269,6 +269,16 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
   shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
 }
 
+// eval-mode ("frozen") BatchNorm statistics in the form the backward kernels take: the conv bias is not in
+// the GEMM, so xhat = (y + bias - running_mean) * invstd = (y - mean_eff) * invstd
+__global__ void bn_eval_stats_kernel(const float* conv_bias, const float* rm, const float* rv, float eps, int C,
+                                     float* mean_eff, float* invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean_eff[c] = rm[c] - (conv_bias ? conv_bias[c] : 0.f);
+  invstd[c] = 1.f / sqrtf(rv[c] + eps);
+}
+
 // ---------------------------------------------------------------------------
 // BN apply + ReLU
 // ---------------------------------------------------------------------------
@@ -549,6 +559,23 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int P, int C,
   const double Qc = (double)scale[c] * c1 - Pc * (double)mean[c];
   coef[c] = (float)Pc;
   coef[C + c] = (float)Qc;
+}
+
+// Backward through an eval-mode BatchNorm (running statistics are constants): dy = scale * g, so the apply
+// coefficients are zero; dgamma = sum g*xhat, dbeta = sum g, and the conv bias (no longer cancelled by a batch
+// mean) gets dbias = sum dy = scale * sum g.
+__global__ void __launch_bounds__(kFinThreads)
+bn_bwd_finalize_frozen_kernel(const float* __restrict__ partials, int P, int C,
+                              const float* __restrict__ scale, float* dgamma, float* dbeta, float* dbias,
+                              float* coef) {
+  double s, q;
+  if (!column_sums_32(partials, P, C, s, q)) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (dbeta) dbeta[c] = (float)s;
+  if (dgamma) dgamma[c] = (float)q;
+  if (dbias) dbias[c] = (float)((double)scale[c] * s);
+  coef[c] = 0.f;
+  coef[C + c] = 0.f;
 }
 
 __global__ void bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, long ldda,
@@ -1110,6 +1137,22 @@ int fpb200_bn_bwd_finalize(const float* partials, int num_partials, int C, doubl
   bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, (cudaStream_t)stream>>>(
       partials, num_partials, C, count, scale, save_mean, save_invstd, dgamma, dbeta, coef);
   return check_launch("bn_bwd_finalize");
+}
+
+int fpb200_bn_eval_stats(const float* conv_bias, const float* running_mean, const float* running_var,
+                         float eps, int C, float* mean_eff, float* invstd, void* stream) {
+  if (C < 1) return FPB200_ERR_SHAPE;
+  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(conv_bias, running_mean, running_var,
+                                                                         eps, C, mean_eff, invstd);
+  return check_launch("bn_eval_stats");
+}
+
+int fpb200_bn_bwd_finalize_frozen(const float* partials, int num_partials, int C, const float* scale,
+                                  float* dgamma, float* dbeta, float* dbias, float* coef, void* stream) {
+  if (C < 1 || num_partials < 1) return FPB200_ERR_SHAPE;
+  bn_bwd_finalize_frozen_kernel<<<(C + 31) / 32, kFinThreads, 0, (cudaStream_t)stream>>>(partials, num_partials, C, scale,
+                                                                                  dgamma, dbeta, dbias, coef);
+  return check_launch("bn_bwd_finalize_frozen");
 }
 
 int fpb200_bn_relu_bwd_apply(const void* da, long ldda, const void* y, long ldy, void* dy,

@@ -199,6 +199,7 @@ class ForwardState:
     """Everything backward needs (owned by the autograd node)."""
     n: int = 0
     sizes: List[Tuple[int, int]] = field(default_factory=list)
+    frozen: bool = False            # forward ran with eval-mode (running-statistics) BatchNorm
     layers: List[LayerSaved] = field(default_factory=list)          # UNet / decoder / single encoder
     pool_idx: List[torch.Tensor] = field(default_factory=list)
     head_in: Optional[torch.Tensor] = None
@@ -216,6 +217,9 @@ class _Fwd:
         self.n, self.sizes, self.dev = n, sizes, dev
         self.params, self.buffers = params, buffers
         self.training, self.save = training, save
+        # eval-mode forward that must be differentiable ("frozen BatchNorm"): the two-pass training schedule
+        # (raw conv output kept, normalise + ReLU as its own pass) with the running statistics as constants
+        self.frozen = save and not training
         self.bf = dict(dtype=torch.bfloat16, device=dev)
         self.f32 = dict(dtype=torch.float32, device=dev)
         self.launches = 0
@@ -233,9 +237,10 @@ class _Fwd:
 class _Bwd:
     """Per-call backward context: the flat gradient slab and its bookkeeping."""
 
-    def __init__(self, n, sizes, dev, params, layout, total):
+    def __init__(self, n, sizes, dev, params, layout, total, frozen=False):
         self.n, self.sizes, self.dev = n, sizes, dev
         self.params = params
+        self.frozen = frozen
         self.bf = dict(dtype=torch.bfloat16, device=dev)
         self.f32 = dict(dtype=torch.float32, device=dev)
         self.layout, self.total = layout, total
@@ -340,18 +345,26 @@ class _Schedule:
         scale = torch.empty(s.cout, **fw.f32)
         shift = torch.empty(s.cout, **fw.f32)
         a = out_view if out_view is not None else torch.empty((n, hh, ww, s.cout), **fw.bf)
-        if fw.training:
-            _RawWriteEpochs.bn += 1    # running statistics are about to be rewritten by a kernel
+        if fw.training or fw.frozen:
             y = torch.empty((n, hh, ww, s.cout), **fw.bf)
-            parts = torch.empty((fw.stat_rows, 2, s.cout), **fw.f32)
-            self._timed("fprop", s, n, hh * ww,
-                        lambda: ops.conv3x3_fprop(xin, wp, y, stat_partials=parts))
             mean = torch.empty(s.cout, **fw.f32)
             invstd = torch.empty(s.cout, **fw.f32)
-            ops.bn_stats_finalize(parts, n * hh * ww, gamma, beta, bias, BN_EPS, BN_MOMENTUM,
-                                  buffers[f"{s.bn}.running_mean"], buffers[f"{s.bn}.running_var"],
-                                  scale, shift, mean, invstd)
-            fw.nbt.append(buffers[f"{s.bn}.num_batches_tracked"])
+            if fw.training:
+                _RawWriteEpochs.bn += 1    # running statistics are about to be rewritten by a kernel
+                parts = torch.empty((fw.stat_rows, 2, s.cout), **fw.f32)
+                self._timed("fprop", s, n, hh * ww,
+                            lambda: ops.conv3x3_fprop(xin, wp, y, stat_partials=parts))
+                ops.bn_stats_finalize(parts, n * hh * ww, gamma, beta, bias, BN_EPS, BN_MOMENTUM,
+                                      buffers[f"{s.bn}.running_mean"], buffers[f"{s.bn}.running_var"],
+                                      scale, shift, mean, invstd)
+                fw.nbt.append(buffers[f"{s.bn}.num_batches_tracked"])
+            else:
+                # frozen: raw conv output, coefficients folded from the running statistics (conv bias included in
+                # the shift); nothing is written to the BatchNorm buffers
+                rm, rv = buffers[f"{s.bn}.running_mean"], buffers[f"{s.bn}.running_var"]
+                self._timed("fprop", s, n, hh * ww, lambda: ops.conv3x3_fprop(xin, wp, y))
+                ops.bn_fold_eval(gamma, beta, bias, rm, rv, BN_EPS, scale, shift)
+                ops.bn_eval_stats(bias, rm, rv, BN_EPS, mean, invstd)
             if defer_apply:
                 a = None
             elif pool_to is not None:
@@ -439,7 +452,7 @@ class _Schedule:
             fw.launches += 1
             self._tr("upsample_concat", level=lvl, x=cur, cat=cat[lvl], c=c)
             cur = self._conv_bn_relu(fw, specs[li], specs[li].cin, cat[lvl], None, None, layers, None); li += 1
-            if lvl == 0 and fw.training and head:
+            if lvl == 0 and (fw.training or fw.frozen) and head:
                 # last layer: its normalise+ReLU is fused into the head kernel (forward) and its
                 # BatchNorm-backward reduction into the head backward -- no activation is stored
                 cur, head_scale, head_shift = self._conv_bn_relu(fw, specs[li], specs[li].cin, cur, None,
@@ -460,9 +473,9 @@ class _Schedule:
         return logits, cur
 
     # ----------------------------------------------------------------------------- backward
-    def _begin_backward(self, n, sizes, dev, params, wgrad_shapes) -> _Bwd:
+    def _begin_backward(self, n, sizes, dev, params, wgrad_shapes, frozen: bool = False) -> _Bwd:
         layout, total = self.grad_layout(params)
-        bw = _Bwd(n, sizes, dev, params, layout, total)
+        bw = _Bwd(n, sizes, dev, params, layout, total, frozen)
         if self.overlap_wgrad and self.conv_events is None:
             if self._side_stream is None or self._side_stream.device != dev:
                 self._side_stream = torch.cuda.Stream(device=dev)
@@ -514,8 +527,13 @@ class _Schedule:
             parts = torch.empty((bw.bn_rows, 2, s.cout), **bw.f32)
             ops.bn_relu_bwd_reduce(da, sv.y, sv.scale, sv.shift, sv.mean, sv.invstd, parts)
         coef = torch.empty((2, s.cout), **bw.f32)
-        ops.bn_bwd_finalize(parts, n * hh * ww, sv.scale, sv.mean, sv.invstd,
-                            grads[f"{s.bn}.weight"], grads[f"{s.bn}.bias"], coef)
+        if bw.frozen:
+            # eval-mode BatchNorm: dy = scale * g, and the conv bias gets a real gradient (sum dy)
+            ops.bn_bwd_finalize_frozen(parts, sv.scale, grads[f"{s.bn}.weight"], grads[f"{s.bn}.bias"],
+                                       grads[f"{s.conv}.bias"], coef)
+        else:
+            ops.bn_bwd_finalize(parts, n * hh * ww, sv.scale, sv.mean, sv.invstd,
+                                grads[f"{s.bn}.weight"], grads[f"{s.bn}.bias"], coef)
         dy = torch.empty((n, hh, ww, s.cout), **bw.bf)
         ops.bn_relu_bwd_apply(da, sv.y, dy, sv.scale, sv.shift, coef)
         if bw.side is not None:
@@ -680,7 +698,7 @@ class UNetEngine(_Schedule):
                     f"{[int(t.shape[1]) for t in images]}")
         sizes = self._level_sizes(h, w)
         fw = _Fwd(n, sizes, dev, params, buffers, training, save)
-        st = ForwardState(n=n, sizes=sizes) if save else None
+        st = ForwardState(n=n, sizes=sizes, frozen=fw.frozen) if save else None
         layers = st.layers if save else None
         pool_idx = st.pool_idx if save else None
 
@@ -700,7 +718,7 @@ class UNetEngine(_Schedule):
         """Returns {param name: fp32 gradient view} (views of one flat slab)."""
         n, sizes = st.n, st.sizes
         bw = self._begin_backward(n, sizes, dlogits.device, params,
-                                  self._wgrad_ws_bytes(n, sizes, self.specs, self.cin_pad))
+                                  self._wgrad_ws_bytes(n, sizes, self.specs, self.cin_pad), st.frozen)
         ne = len(self.enc_specs)
         dcat, d_x5 = self._decoder_backward(bw, self.dec_specs, st.layers[ne:], st.head_in, dlogits, "",
                                             self.n_classes)
@@ -739,7 +757,7 @@ class EncoderEngine(_Schedule):
         dev, n, h, w = _check_images(images, self.n_channels)
         sizes = self._level_sizes(h, w)
         fw = _Fwd(n, sizes, dev, params, buffers, training, save)
-        st = ForwardState(n=n, sizes=sizes) if save else None
+        st = ForwardState(n=n, sizes=sizes, frozen=fw.frozen) if save else None
         x = ops.ingest(images, self.cin_pad)
         fw.launches += 1
         feats = [torch.empty((n, sizes[l][0], sizes[l][1], FEAT_CH[l]), **fw.bf) for l in range(5)]
@@ -752,7 +770,7 @@ class EncoderEngine(_Schedule):
         """d_feats: NHWC bf16 gradients of the five features."""
         n, sizes = st.n, st.sizes
         bw = self._begin_backward(n, sizes, d_feats[0].device, params,
-                                  self._wgrad_ws_bytes(n, sizes, self.specs, self.cin_pad))
+                                  self._wgrad_ws_bytes(n, sizes, self.specs, self.cin_pad), st.frozen)
         self._encoder_backward(bw, self.specs, st.layers, st.pool_idx, self.cin_pad, d_feats[4],
                                lambda lvl: d_feats[lvl])
         self._finish_backward(bw)
@@ -786,7 +804,7 @@ class DecoderEngine(_Schedule):
                 raise RuntimeError(f"floodplanet_b200: feature {l} has shape {tuple(f.shape)}, expected "
                                    f"{(n, FEAT_CH[l], sizes[l][0], sizes[l][1])}")
         fw = _Fwd(n, sizes, dev, params, buffers, training, save)
-        st = ForwardState(n=n, sizes=sizes) if save else None
+        st = ForwardState(n=n, sizes=sizes, frozen=fw.frozen) if save else None
         cat = self._alloc_cat(fw)
         for l in range(4):
             ops.nchw_f32_to_nhwc_bf16(feats_nchw[l], cat[l][..., :ENC_CH[l]])
@@ -804,7 +822,7 @@ class DecoderEngine(_Schedule):
         """Returns (grads, slab, [d_x1..d_x5] as NHWC bf16 views)."""
         n, sizes = st.n, st.sizes
         bw = self._begin_backward(n, sizes, dlogits.device, params,
-                                  self._wgrad_ws_bytes(n, sizes, self.specs, 0))
+                                  self._wgrad_ws_bytes(n, sizes, self.specs, 0), st.frozen)
         dcat, d_x5 = self._decoder_backward(bw, self.specs, st.layers, st.head_in, dlogits, self.prefix,
                                             self.n_classes)
         self._finish_backward(bw)
@@ -871,7 +889,7 @@ class LateFusionEngine(_Schedule):
                     "fusion convs by len(in_channels))")
         sizes = self._level_sizes(h, w)
         fw = _Fwd(n, sizes, dev, params, buffers, training, save)
-        st = ForwardState(n=n, sizes=sizes) if save else None
+        st = ForwardState(n=n, sizes=sizes, frozen=fw.frozen) if save else None
         fused_in = [torch.empty((n, sizes[l][0], sizes[l][1], FEAT_CH[l] * k), **fw.bf) for l in range(5)]
         for m, name in enumerate(order):
             x = ops.ingest([images[name]], self.cin_pad[name])
@@ -910,7 +928,7 @@ class LateFusionEngine(_Schedule):
             ws_bytes += self._wgrad_ws_bytes(n, sizes, self.enc_specs[name], self.cin_pad[name])
         ws_bytes += [ops.conv1x1_wgrad_workspace_bytes(n, sizes[l][0], sizes[l][1], FEAT_CH[l] * k, FEAT_CH[l])
                      for l in range(5)]
-        bw = self._begin_backward(n, sizes, dlogits.device, params, ws_bytes)
+        bw = self._begin_backward(n, sizes, dlogits.device, params, ws_bytes, st.frozen)
         dcat, d_x5 = self._decoder_backward(bw, self.dec_specs, st.layers, st.head_in, dlogits, "decoder.",
                                             self.n_classes)
         # fusion convs, levels 4..0 (reverse forward order = slab order)

@@ -26,7 +26,8 @@ class _LateFusionFunction(torch.autograd.Function):
         images = dict(zip(keys, tensors[:n_images]))
         plist = tensors[n_images:]
         params = dict(zip(engine.names, plist))
-        logits, st = engine.forward(images, params, module._engine_buffers(), training=True, save=True)
+        logits, st = engine.forward(images, params, module._engine_buffers(), training=module.decoder.training,
+                                    save=True)
         ctx.engine, ctx.state, ctx.n_images = engine, st, n_images
         ctx.save_for_backward(*plist)
         return logits
@@ -114,8 +115,7 @@ class LateFusionModel(WaterSegmentationModel):
         engine = self._engine
         params = self._engine_params()
         training = self.decoder.training
-        needs_grad = (torch.is_grad_enabled() and training
-                      and any(p.requires_grad for p in params.values()))
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params.values())
         if needs_grad:
             return _LateFusionFunction.apply(self, keys, *images, *[params[n] for n in engine.names])
         with torch.no_grad():

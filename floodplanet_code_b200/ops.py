@@ -294,6 +294,20 @@ def bn_fold_eval(gamma, beta, conv_bias, running_mean, running_var, eps, scale, 
     capi.check(st, "bn_fold_eval", C=c)
 
 
+def bn_eval_stats(conv_bias, running_mean, running_var, eps, mean_eff, invstd) -> None:
+    c = running_mean.numel()
+    st = _lib().fpb200_bn_eval_stats(_ptr(conv_bias), running_mean.data_ptr(), running_var.data_ptr(), eps, c,
+                                     mean_eff.data_ptr(), invstd.data_ptr(), _stream())
+    capi.check(st, "bn_eval_stats", C=c)
+
+
+def bn_bwd_finalize_frozen(partials, scale, dgamma, dbeta, dbias, coef) -> None:
+    c = scale.numel()
+    st = _lib().fpb200_bn_bwd_finalize_frozen(partials.data_ptr(), partials.shape[0], c, scale.data_ptr(),
+                                              _ptr(dgamma), _ptr(dbeta), _ptr(dbias), coef.data_ptr(), _stream())
+    capi.check(st, "bn_bwd_finalize_frozen", C=c)
+
+
 def bn_apply_relu(y, a, scale, shift) -> None:
     yp, ldy = nhwc_view(y)
     ap, lda = nhwc_view(a)

@@ -80,7 +80,8 @@ class _UNetFunction(torch.autograd.Function):
         engine = module._engine
         params = dict(zip(engine.names, plist))
         buffers = dict(module.named_buffers())
-        logits, st = engine.forward(images, params, buffers, training=True, save=True)
+        # module.training False = eval-mode (running-statistics) BatchNorm that stays differentiable
+        logits, st = engine.forward(images, params, buffers, training=module.training, save=True)
         ctx.engine = engine
         ctx.state = st
         ctx.n_images = n_images
@@ -145,14 +146,12 @@ class UNet(nn.Module):
                     "inference scripts never ask for one) -- detach the input")
         engine = self._engine
         params = dict(self.named_parameters())
-        needs_grad = (torch.is_grad_enabled() and self.training
-                      and any(p.requires_grad for p in params.values()))
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params.values())
         if needs_grad:
+            # train(): batch-statistics BatchNorm; eval() with grad mode on: the same differentiable schedule
+            # with the running statistics as constants (frozen-BatchNorm fine-tuning; the reference's modules
+            # support autograd in eval mode too).  Validation / infer / predict run under no_grad -> below.
             return _UNetFunction.apply(self, len(images), *images, *[params[n] for n in engine.names])
-        # eval mode (or no_grad): forward only.  Backward through running-statistics BatchNorm is not
-        # built (no caller in the reference differentiates an eval-mode forward: validation / infer /
-        # predict all run under no_grad); the logits carry no graph, so a `.backward()` on them fails
-        # loudly in torch rather than training nothing.  See INTEGRATION.md section 7 "Limits".
         with torch.no_grad():
             logits, _ = engine.forward(images, params, dict(self.named_buffers()),
                                        training=self.training, save=False)
@@ -196,7 +195,7 @@ class _EncoderFunction(torch.autograd.Function):
     def forward(ctx, module, engine, n_images, *tensors):
         images, plist = tensors[:n_images], tensors[n_images:]
         params = dict(zip(engine.names, plist))
-        feats, st = engine.forward(images, params, dict(module.named_buffers()), training=True, save=True)
+        feats, st = engine.forward(images, params, dict(module.named_buffers()), training=module.training, save=True)
         ctx.engine, ctx.state, ctx.n_images = engine, st, n_images
         ctx.save_for_backward(*plist)
         return tuple(ops.nhwc_bf16_to_nchw_f32(f) for f in feats)
@@ -227,7 +226,7 @@ class _DecoderFunction(torch.autograd.Function):
     def forward(ctx, module, engine, *tensors):
         feats, plist = tensors[:5], tensors[5:]
         params = dict(zip(engine.names, plist))
-        logits, st = engine.forward(feats, params, dict(module.named_buffers()), training=True, save=True)
+        logits, st = engine.forward(feats, params, dict(module.named_buffers()), training=module.training, save=True)
         ctx.engine, ctx.state = engine, st
         ctx.save_for_backward(*plist)
         return logits
@@ -250,7 +249,7 @@ def _run_encoder_module(module: nn.Module, engine: EncoderEngine, images):
     _check_cuda_nchw(images)
     params = dict(module.named_parameters())
     plist = [params[n] for n in engine.names]
-    if torch.is_grad_enabled() and module.training and any(p.requires_grad for p in plist):
+    if torch.is_grad_enabled() and any(p.requires_grad for p in plist):
         return list(_EncoderFunction.apply(module, engine, len(images), *images, *plist))
     with torch.no_grad():
         feats, _ = engine.forward(images, params, dict(module.named_buffers()),
@@ -263,7 +262,7 @@ def _run_decoder_module(module: nn.Module, engine: DecoderEngine, feats, head: b
     _check_cuda_nchw(feats)
     params = dict(module.named_parameters())
     plist = [params[n] for n in engine.names]
-    needs_grad = torch.is_grad_enabled() and module.training and (
+    needs_grad = torch.is_grad_enabled() and (
         any(p.requires_grad for p in plist) or any(f.requires_grad for f in feats))
     if needs_grad:
         if not head:

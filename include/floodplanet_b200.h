@@ -135,6 +135,19 @@ int fpb200_bn_fold_eval(const float* gamma, const float* beta, const float* conv
                         const float* running_mean, const float* running_var, float eps, int C,
                         float* scale, float* shift, void* stream);
 
+/* Backward THROUGH an eval-mode BatchNorm (frozen-BatchNorm fine-tuning, saliency: the reference's nn.BatchNorm2d
+ * supports autograd in .eval(), models/unet.py:15,17).  The running statistics are constants, so with
+ * xhat = (y + conv_bias - running_mean) * invstd:
+ *   fpb200_bn_eval_stats          mean_eff = running_mean - conv_bias, invstd = 1/sqrt(running_var + eps)
+ *                                 (the form fpb200_bn_relu_bwd_reduce and the fused reductions take)
+ *   fpb200_bn_bwd_finalize_frozen dgamma = sum g*xhat, dbeta = sum g, dbias = scale * sum g (the conv bias is no
+ *                                 longer cancelled by a batch mean), coef = 0 so that fpb200_bn_relu_bwd_apply
+ *                                 produces dy = scale * g.  partials as for fpb200_bn_bwd_finalize. */
+int fpb200_bn_eval_stats(const float* conv_bias, const float* running_mean, const float* running_var,
+                         float eps, int C, float* mean_eff, float* invstd, void* stream);
+int fpb200_bn_bwd_finalize_frozen(const float* partials, int num_partials, int C, const float* scale,
+                                  float* dgamma, float* dbeta, float* dbias, float* coef, void* stream);
+
 /* a = relu(y*scale+shift) elementwise over an NHWC bf16 view. */
 int fpb200_bn_apply_relu(const void* y, long ldy, void* a, long lda, const float* scale,
                          const float* shift, long num_pixels, int C, void* stream);

@@ -41,7 +41,7 @@ def decode_pool_idx(idx_nhwc, h, w):
     return hh * w + ww
 
 
-def check_forward(m, sd0, batch, logits, trace, report):
+def check_forward(m, sd0, batch, logits, trace, report, frozen=False):
     """Walk the forward records in the order of unet.py:100-111."""
     params = {k: v.detach() for k, v in m.named_parameters()}
     fwd = [r for r in trace if r["op"] in ("conv_bn_relu", "upsample_concat", "head")]
@@ -74,19 +74,29 @@ def check_forward(m, sd0, batch, logits, trace, report):
             assert e < FWD_TOL, (s.conv, e)
             # BatchNorm statistics + normalise + ReLU on the kernel's own (stored) conv output
             yf = f32c(y)
-            rm = torch.zeros(s.cout, device=y.device)
-            rv = torch.ones(s.cout, device=y.device)
-            a_ref = F.relu(F.batch_norm(yf + bias[None, :, None, None], rm, rv, gamma, beta, True, BN_MOM, BN_EPS))
-            mean_ref = yf.mean((0, 2, 3))
-            var_ref = yf.var((0, 2, 3), unbiased=False)
-            assert rel(r["mean"], mean_ref) < 1e-3 or float((r["mean"] - mean_ref).abs().max()) < 1e-5, s.bn
-            assert rel(r["invstd"], torch.rsqrt(var_ref + BN_EPS)) < 1e-3, s.bn
-            # running statistics after ONE step from the default (0, 1) buffers; conv bias enters the mean
             bufs = dict(m.named_buffers())
-            assert sd0[f"{s.bn}.running_mean"].abs().max() == 0 and (sd0[f"{s.bn}.running_var"] == 1).all()
-            assert rel(bufs[f"{s.bn}.running_mean"], rm) < 1e-3 or float((bufs[f"{s.bn}.running_mean"] - rm).abs().max()) < 1e-6, s.bn
-            assert rel(bufs[f"{s.bn}.running_var"], rv) < 1e-3, s.bn
-            assert int(bufs[f"{s.bn}.num_batches_tracked"]) == 1
+            if frozen:
+                # eval-mode BatchNorm: running statistics are constants and must be untouched by the step
+                rm0, rv0 = sd0[f"{s.bn}.running_mean"], sd0[f"{s.bn}.running_var"]
+                assert torch.equal(bufs[f"{s.bn}.running_mean"], rm0) and torch.equal(bufs[f"{s.bn}.running_var"], rv0)
+                assert int(bufs[f"{s.bn}.num_batches_tracked"]) == int(sd0[f"{s.bn}.num_batches_tracked"])
+                a_ref = F.relu(F.batch_norm(yf + bias[None, :, None, None], rm0.clone(), rv0.clone(), gamma, beta,
+                                            False, BN_MOM, BN_EPS))
+                assert rel(r["mean"], rm0 - bias) < 1e-5 or float((r["mean"] - (rm0 - bias)).abs().max()) < 1e-6, s.bn
+                assert rel(r["invstd"], torch.rsqrt(rv0 + BN_EPS)) < 1e-5, s.bn
+            else:
+                rm = torch.zeros(s.cout, device=y.device)
+                rv = torch.ones(s.cout, device=y.device)
+                a_ref = F.relu(F.batch_norm(yf + bias[None, :, None, None], rm, rv, gamma, beta, True, BN_MOM, BN_EPS))
+                mean_ref = yf.mean((0, 2, 3))
+                var_ref = yf.var((0, 2, 3), unbiased=False)
+                assert rel(r["mean"], mean_ref) < 1e-3 or float((r["mean"] - mean_ref).abs().max()) < 1e-5, s.bn
+                assert rel(r["invstd"], torch.rsqrt(var_ref + BN_EPS)) < 1e-3, s.bn
+                # running statistics after ONE step from the default (0, 1) buffers; conv bias enters the mean
+                assert sd0[f"{s.bn}.running_mean"].abs().max() == 0 and (sd0[f"{s.bn}.running_var"] == 1).all()
+                assert rel(bufs[f"{s.bn}.running_mean"], rm) < 1e-3 or float((bufs[f"{s.bn}.running_mean"] - rm).abs().max()) < 1e-6, s.bn
+                assert rel(bufs[f"{s.bn}.running_var"], rv) < 1e-3, s.bn
+                assert int(bufs[f"{s.bn}.num_batches_tracked"]) == 1
             if r["a"] is not None:
                 e = rel(f32c(r["a"]), a_ref)
                 report.append((f"fwd bn+relu {s.bn}", e))
@@ -128,7 +138,7 @@ def check_forward(m, sd0, batch, logits, trace, report):
     return by_layer, skips
 
 
-def check_backward(m, batch, logits, loss, trace, fwd_layers, skips, ignore_index, report):
+def check_backward(m, batch, logits, loss, trace, fwd_layers, skips, ignore_index, report, frozen=False):
     params = {k: v.detach() for k, v in m.named_parameters()}
     grads = {k: v.grad.detach() for k, v in m.named_parameters()}
     bwd = [r for r in trace if r["op"] in ("head_bwd", "layer_bwd", "upsample_concat_bwd", "maxpool_bwd")]
@@ -148,7 +158,13 @@ def check_backward(m, batch, logits, loss, trace, fwd_layers, skips, ignore_inde
     last = fwd_layers[17]
     s17 = last["spec"]
     gamma, beta = params[f"{s17.bn}.weight"], params[f"{s17.bn}.bias"]
-    a_last = F.relu(F.batch_norm(f32c(last["y"]), None, None, gamma, beta, True, BN_MOM, BN_EPS))
+    bufs = dict(m.named_buffers())
+    if frozen:
+        a_last = F.relu(F.batch_norm(f32c(last["y"]) + params[f"{s17.conv}.bias"][None, :, None, None],
+                                     bufs[f"{s17.bn}.running_mean"].clone(), bufs[f"{s17.bn}.running_var"].clone(),
+                                     gamma, beta, False, BN_MOM, BN_EPS))
+    else:
+        a_last = F.relu(F.batch_norm(f32c(last["y"]), None, None, gamma, beta, True, BN_MOM, BN_EPS))
     wh = params["outc.conv.weight"]
     dl = head["dlogits"]
     d_act_ref = torch.nn.grad.conv2d_input(a_last.shape, wh, dl)
@@ -177,7 +193,12 @@ def check_backward(m, batch, logits, loss, trace, fwd_layers, skips, ignore_inde
             # BatchNorm(train) + ReLU backward through torch autograd at the kernel's own y and da
             yv = f32c(r["y"]).requires_grad_(True)
             g_, b_ = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
-            a = F.relu(F.batch_norm(yv, None, None, g_, b_, True, BN_MOM, BN_EPS))
+            cb_ = params[f"{s.conv}.bias"].clone().requires_grad_(True)
+            if frozen:
+                a = F.relu(F.batch_norm(yv + cb_[None, :, None, None], bufs[f"{s.bn}.running_mean"].clone(),
+                                        bufs[f"{s.bn}.running_var"].clone(), g_, b_, False, BN_MOM, BN_EPS))
+            else:
+                a = F.relu(F.batch_norm(yv, None, None, g_, b_, True, BN_MOM, BN_EPS))
             a.backward(f32c(da))
             for name, got, ref in (("dy", f32c(r["dy"]), yv.grad), ("dgamma", r["dgamma"], g_.grad),
                                    ("dbeta", r["dbeta"], b_.grad)):
@@ -194,8 +215,14 @@ def check_backward(m, batch, logits, loss, trace, fwd_layers, skips, ignore_inde
             report.append((f"bwd {s.conv} dW", e))
             assert e < GRAD_TOL, (s.conv, "dW", e)
             assert torch.equal(r["dw"], grads[f"{s.conv}.weight"])
-            # conv bias feeding a training-mode BatchNorm: exactly cancelled (reference: rounding noise)
-            assert float(grads[f"{s.conv}.bias"].abs().max()) == 0.0
+            if frozen:
+                # eval-mode BatchNorm does not cancel the conv bias: d bias = sum over pixels of dy
+                e = rel(grads[f"{s.conv}.bias"], cb_.grad)
+                report.append((f"bwd {s.conv} dbias", e))
+                assert e < GRAD_TOL, (s.conv, "dbias", e)
+            else:
+                # conv bias feeding a training-mode BatchNorm: exactly cancelled (reference: rounding noise)
+                assert float(grads[f"{s.conv}.bias"].abs().max()) == 0.0
             if tag == 0:
                 assert r["dx"] is None          # no gradient into the image
             else:
@@ -243,7 +270,7 @@ def check_backward(m, batch, logits, loss, trace, fwd_layers, skips, ignore_inde
 
 
 
-def walk(m, sd0, batch, logits, loss, trace, ignore_index, fwd_tol=None, grad_tol=None):
+def walk(m, sd0, batch, logits, loss, trace, ignore_index, fwd_tol=None, grad_tol=None, frozen=False):
     """Full forward + backward walk.  Returns the list of (what, relative error) comparisons made;
     raises AssertionError at the first step outside tolerance or mis-wired.  Tolerances default to
     the north_star's (1e-2 forward, 2e-2 gradients); callers may tighten them towards the bf16
@@ -253,15 +280,17 @@ def walk(m, sd0, batch, logits, loss, trace, ignore_index, fwd_tol=None, grad_to
     FWD_TOL = saved[0] if fwd_tol is None else fwd_tol
     GRAD_TOL = saved[1] if grad_tol is None else grad_tol
     try:
-        return _walk(m, sd0, batch, logits, loss, trace, ignore_index)
+        return _walk(m, sd0, batch, logits, loss, trace, ignore_index, frozen)
     finally:
         FWD_TOL, GRAD_TOL = saved
 
 
-def _walk(m, sd0, batch, logits, loss, trace, ignore_index):
+def _walk(m, sd0, batch, logits, loss, trace, ignore_index, frozen=False):
+    """frozen: the step ran with the module in eval() and grad mode on -- BatchNorm uses the running statistics as
+    constants (F.batch_norm(training=False)), its buffers must not change, and the conv biases get real gradients."""
     report = []
-    fwd_layers, skips = check_forward(m, sd0, batch, logits, trace, report)
-    check_backward(m, batch, logits, loss, trace, fwd_layers, skips, ignore_index, report)
+    fwd_layers, skips = check_forward(m, sd0, batch, logits, trace, report, frozen)
+    check_backward(m, batch, logits, loss, trace, fwd_layers, skips, ignore_index, report, frozen)
     asserted = [k for k, _ in report if k.endswith(" dW") or "dgamma" in k or "dbeta" in k or k == "bwd head db"]
     assert len(asserted) == 18 * 3 + 2, "every trainable parameter's gradient must have been compared"
     return report

@@ -92,3 +92,50 @@ def test_trace_is_off_by_default_and_costs_nothing():
     x = torch.rand(1, 4, 32, 32, device="cuda")
     out = m(x)
     assert m._engine.trace is None and out.shape == (1, 3, 32, 32)
+
+
+@pytest.mark.parametrize("n,c_in,h,w", [(2, 4, 64, 64), (1, 4, 300, 300)])
+def test_eval_mode_with_grad_is_differentiable_frozen_batchnorm(n, c_in, h, w):
+    """Module in eval() with grad mode on (frozen-BatchNorm fine-tuning; the reference's nn.BatchNorm2d supports
+    autograd in eval mode): the same per-step walk with F.batch_norm(training=False) as the oracle op.  BatchNorm
+    buffers must stay untouched, conv biases get real gradients (18 extra comparisons)."""
+    from floodplanet_code_b200.loss import MaskedCrossEntropyLoss
+    from floodplanet_code_b200.unet import UNet
+    sd = O.init_state_dict(c_in, 3, seed=7)
+    m = UNet(c_in, 3)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    b = O.synthetic_batch(n, c_in, h, w, seed=8, block=8 if h < 128 else 20, device="cuda")
+    with torch.no_grad():
+        for _ in range(3):
+            m(b["image"])                       # non-trivial running statistics
+    m.eval()
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    eng = m._engine
+    eng.trace = []
+    try:
+        logits = m(b["image"])
+        assert logits.requires_grad
+        loss = MaskedCrossEntropyLoss(0)(logits, b["target"])
+        loss.backward()
+        torch.cuda.synchronize()
+        trace = eng.trace
+    finally:
+        eng.trace = None
+    report = TF.walk(m, sd0, b, logits.detach(), loss.detach(), trace, 0, fwd_tol=TIGHT_FWD_TOL,
+                     grad_tol=TIGHT_GRAD_TOL, frozen=True)
+    assert len(report) >= 140 + 18 and sum(1 for k, _ in report if k.endswith("dbias")) == 18
+    print(f"\nfrozen-BN walk {n}x{c_in}x{h}x{w}: {len(report)} comparisons, worst "
+          f"{max(e for _, e in report):.2e}")
+    # same logits as the folded no_grad inference schedule up to bf16 rounding of the stored conv output,
+    # and the loss agrees with the fp32 oracle in eval mode
+    with torch.no_grad():
+        folded = m(b["image"])
+    assert float((folded - logits).norm() / folded.norm()) < 2e-2
+    ologits = O.unet_forward({k: v.clone() for k, v in sd0.items()}, b["image"], training=False)
+    oloss, _ = O.masked_ce(ologits, b["target"], 0)
+    assert abs(float(loss.detach()) - float(oloss)) <= 1e-2 * abs(float(oloss))
+    # the step left every buffer as it was
+    for k, v in m.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            assert torch.equal(v, sd0[k]), k

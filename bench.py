@@ -329,6 +329,28 @@ def run_ours(args):
     if os.environ.get("FPB200_OVERLAP_WGRAD") == "1":   # experiment switch: wgrads on a second stream
         engine.overlap_wgrad = True
 
+    if args.infer_only:
+        # BASELINE configs[4] alone (sliding-window inference, tiles sharded over the launched ranks), same JSON shape
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        infer = infer_block(model, dev, rank, world, args)
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            print(json.dumps({"metric": "scene_inference_tiles_per_sec", "value": infer["tiles_per_sec"], "unit": "tiles/s",
+                              "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "bf16",
+                              "data": "synthetic", "config": {"workload": infer["workload"]}, "clocks": clocks,
+                              "e2e": {"value": infer["tiles_per_sec"], "unit": "tiles/s",
+                                      "h2d_bytes_per_step": infer["h2d_bytes_per_scene"],
+                                      "d2h_bytes_per_step": infer["d2h_bytes_per_scene"]},
+                              "gpu_launches": infer["gpu_launches_per_scene"], "infer": infer}), flush=True)
+        if world > 1:
+            dist.barrier()
+            if reducer is not None and reducer.comm is not None:
+                reducer.comm.destroy()
+            dist.destroy_process_group()
+        return
+
     # synthetic data: U[0,1) image, blocky int64 target ~58% ignored / 42% flood
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = []
@@ -622,6 +644,7 @@ def main():
     ap.add_argument("--no-allreduce", action="store_true",
                     help="probe: N independent replicas without the gradient exchange (not a training configuration)")
     ap.add_argument("--no-infer", action="store_true", help="skip the configs[4] scene-inference block")
+    ap.add_argument("--infer-only", action="store_true", help="run ONLY the configs[4] scene-inference block")
     ap.add_argument("--infer-scene", type=int, default=10240, help="scene edge in pixels (configs[4]: 10240)")
     ap.add_argument("--infer-tile-batch", type=int, default=20,
                     help="tiles per forward; a multiple of the tiles per scene row (20) copies no row twice")

@@ -103,6 +103,11 @@ def predict_scene(unet: UNet, scene: torch.Tensor, crop: int = 512, stride: Opti
 _COPY_STREAMS = {}
 
 
+def _row_len(tiles, t) -> int:
+    """Number of tiles of `tiles` that start on the same scene row as tile t."""
+    return sum(1 for u in tiles if u[0] == t[0])
+
+
 def _copy_stream(dev) -> "torch.cuda.Stream":
     key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
     if key not in _COPY_STREAMS:
@@ -147,7 +152,16 @@ def predict_scene_from_host(unet: UNet, scene_host: torch.Tensor, crop: int = 51
         weight = torch.zeros((r1 - r0, W), dtype=torch.float32, device=dev)
         # host -> device copies run on their own stream, one tile batch ahead of the compute stream
         # (two row-band buffers, events both ways), so PCIe time hides behind the UNet of the previous batch
-        batches = [mine[b0:b0 + tile_batch] for b0 in range(0, len(mine), tile_batch)]
+        # batches end on tile-row boundaries (tiles of one batch share as few scene rows as possible with the
+        # next one): no scene row is copied twice, and the first -- un-hidden -- copy stays small
+        batches, cur = [], []
+        for t in mine:
+            if cur and (len(cur) >= tile_batch or (t[0] != cur[-1][0] and len(cur) + _row_len(mine, t) > tile_batch)):
+                batches.append(cur)
+                cur = []
+            cur.append(t)
+        if cur:
+            batches.append(cur)
         spans = [(min(t[0] for t in ch), min(H, max(t[0] + t[2] for t in ch))) for ch in batches]
         max_rows = max(e - s0 for s0, e in spans)
         bufs = [torch.empty((c, max_rows, W), dtype=torch.float32, device=dev) for _ in range(min(2, len(batches)))]

@@ -326,8 +326,8 @@ def run_ours(args):
                if world > 1 and not args.no_allreduce else None)
     dp_check = data_parallel_check(model, reducer, dev, rank, world, args) if reducer is not None else None
     engine = model.model._engine
-    if os.environ.get("FPB200_OVERLAP_WGRAD") == "1":   # experiment switch: wgrads on a second stream
-        engine.overlap_wgrad = True
+    if os.environ.get("FPB200_OVERLAP_WGRAD") in ("0", "1"):   # A/B switch: wgrads on a second stream
+        engine.overlap_wgrad = os.environ["FPB200_OVERLAP_WGRAD"] == "1"
 
     if args.infer_only:
         # BASELINE configs[4] alone (sliding-window inference, tiles sharded over the launched ranks), same JSON shape

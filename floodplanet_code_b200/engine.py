@@ -263,19 +263,21 @@ class _Schedule:
 
     def __init__(self):
         self.packed = PackedWeights()
-        # optional hook(flat_grad_slab, start, end): called in backward as soon as the grads
-        # in slab[start:end] are final (used for bucketed data-parallel all-reduce)
-        self.grad_ready_hook: Optional[Callable[[torch.Tensor, int, int], None]] = None
+        # optional hook(flat_grad_slab, start, end, side_stream): called in backward as soon as the grads
+        # in slab[start:end] are final = ENQUEUED on the current stream and, for weight gradients when
+        # wgrads overlap, on side_stream (None otherwise); used for the bucketed data-parallel all-reduce
+        self.grad_ready_hook: Optional[Callable] = None
         # optional hook(flat_grad_slab, total): called once at the end of backward
         self.grad_done_hook: Optional[Callable[[torch.Tensor, int], None]] = None
         # optional profiler: when a list, (tag, flops, start_event, end_event) per conv launch
         self.conv_events: Optional[list] = None
-        # backward: optionally run every wgrad on a second stream.  wgrad is off the critical path
-        # (only the optimiser needs dW) and could overlap the HBM-bound BatchNorm-backward passes
-        # of the next layer.  Measured on B200 at batch 64: <= 1 % gain (both kernels are persistent
-        # and the step is power-capped, so overlap buys no energy) and more run-to-run variance
-        # from cross-stream allocator bookkeeping -- off by default.
-        self.overlap_wgrad = False
+        # backward: every wgrad runs on a second stream.  wgrad is off the critical path (only the
+        # optimiser needs dW) and overlaps the HBM-bound BatchNorm-backward passes of the next layer.
+        # The step is power-capped, so the overlap raises power and lowers the SM clock (1608 -> 1567 MHz);
+        # net gain measured in round 2 on one box, alternating A/B, 3 x 30 steps each: 900.8 -> 912.3
+        # chips/s (+1.3 %), end to end 892 -> 908 (+1.8 %), every overlapped run above every serial one
+        # (profiles/r02_wgrad_overlap_ab.md).  Set False for a strictly single-stream backward.
+        self.overlap_wgrad = True
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._fold_cache: Dict[str, Tuple[tuple, torch.Tensor, torch.Tensor]] = {}
         self.launches = 0  # kernels launched by the last forward/backward (for bench accounting)
@@ -494,9 +496,9 @@ class _Schedule:
         o, nel = bw.layout[name_last]
         end = (o + nel + 3) // 4 * 4
         if self.grad_ready_hook is not None and end > bw.ready_upto:
-            if bw.side is not None:
-                bw.main.wait_stream(bw.side)   # weight grads of this bucket come from the side stream
-            self.grad_ready_hook(bw.slab, bw.ready_upto, end)
+            # weight grads come from the side stream when wgrads overlap: the hook gets that stream and orders its
+            # collective after BOTH producers (the main stream is not made to wait for wgrad here)
+            self.grad_ready_hook(bw.slab, bw.ready_upto, end, bw.side)
         bw.ready_upto = max(bw.ready_upto, end)
 
     def _finish_backward(self, bw: _Bwd) -> None:

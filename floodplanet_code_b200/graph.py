@@ -28,6 +28,9 @@ class GraphedTrainStep:
         engine = module.model._engine
         if engine.grad_ready_hook is not None:
             raise RuntimeError("GraphedTrainStep: capture with a gradient all-reduce hook is not supported")
+        # one captured stream: the wgrad side stream's allocator bookkeeping (record_stream) does not belong in a
+        # capture, and inside a graph the kernels are already free of launch gaps
+        engine.overlap_wgrad = False
         self.fwd_launches = 0
         self.bwd_launches = 0
         side = torch.cuda.Stream()

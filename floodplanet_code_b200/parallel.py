@@ -123,15 +123,18 @@ class BucketedGradAllReduce:
         # optional per-bucket timeline: when a list, (start, end, ready_evt, begin_evt, end_evt) per bucket
         self.timeline: Optional[list] = None
 
-    def _launch(self, slab: torch.Tensor, start: int, end: int) -> None:
+    def _launch(self, slab: torch.Tensor, start: int, end: int, side=None) -> None:
         piece = slab[start:end]
         if self.comm is not None:
-            # producer (compute stream) -> event -> communication stream -> collective -> event
+            # producers (compute stream, and the wgrad side stream when wgrads overlap) -> events ->
+            # communication stream -> collective -> event
             compute = torch.cuda.current_stream(slab.device)
             ready = torch.cuda.Event(enable_timing=self.timeline is not None)
             ready.record(compute)
             cs = self.comm.stream
             cs.wait_event(ready)
+            if side is not None:
+                cs.wait_stream(side)
             t0 = t1 = None
             if self.timeline is not None:
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -143,6 +146,8 @@ class BucketedGradAllReduce:
                 self.timeline.append((start, end, ready, t0, t1))
             self._pending.append((done, None))
             return
+        if side is not None:
+            torch.cuda.current_stream(slab.device).wait_stream(side)   # c10d orders only against the current stream
         if self._avg:
             work = dist.all_reduce(piece, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             self._pending.append((work, None))
@@ -150,14 +155,14 @@ class BucketedGradAllReduce:
             work = dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._pending.append((work, piece))
 
-    def on_ready(self, slab: torch.Tensor, start: int, end: int) -> None:
+    def on_ready(self, slab: torch.Tensor, start: int, end: int, side=None) -> None:
         if self.world == 1:
             return
         if start == 0:
             self._start = 0
             self.buckets_last_step = 0
         if end - self._start >= self.bucket_elems:
-            self._launch(slab, self._start, end)
+            self._launch(slab, self._start, end, side)
             self._start = end
             self.buckets_last_step += 1
 

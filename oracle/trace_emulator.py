@@ -28,10 +28,11 @@ def _nchw(t):
     return t.permute(0, 3, 1, 2).contiguous()
 
 
-def emulate_traced_step(m, specs, batch, ignore_index, cin_pad, fault=None):
+def emulate_traced_step(m, specs, batch, ignore_index, cin_pad, fault=None, frozen=False):
     """m: a (CPU) module with the reference's parameter / buffer names (the product's container
     classes work); specs: engine.unet_conv_specs(n_channels).  Sets `.grad` on every parameter, updates
-    the BatchNorm buffers, returns (logits, loss, trace).  `fault`: name of a planted bug."""
+    the BatchNorm buffers, returns (logits, loss, trace).  `fault`: name of a planted bug.  `frozen`: eval-mode
+    BatchNorm with autograd (running statistics as constants, buffers untouched, conv biases get gradients)."""
     P = dict(m.named_parameters())
     B = dict(m.named_buffers())
     trace = []
@@ -49,17 +50,22 @@ def emulate_traced_step(m, specs, batch, ignore_index, cin_pad, fault=None):
         w = _bf(P[f"{s.conv}.weight"].detach()).float()
         y = _bf(_nhwc(F.conv2d(_nchw(xin[..., :s.cin].float()), w, None, padding=1)))
         yf = y.float()
-        mean = yf.mean((0, 1, 2))
-        var = yf.var((0, 1, 2), unbiased=False)
-        cnt = yf.numel() / yf.shape[3]
-        invstd = torch.rsqrt(var + BN_EPS)
         gamma, beta = P[f"{s.bn}.weight"].detach(), P[f"{s.bn}.bias"].detach()
+        if frozen:
+            cb = P[f"{s.conv}.bias"].detach()
+            mean = B[f"{s.bn}.running_mean"].detach() - (0.0 if fault == "frozen_bias_dropped" else cb)
+            invstd = torch.rsqrt(B[f"{s.bn}.running_var"].detach() + BN_EPS)
+        else:
+            mean = yf.mean((0, 1, 2))
+            var = yf.var((0, 1, 2), unbiased=False)
+            cnt = yf.numel() / yf.shape[3]
+            invstd = torch.rsqrt(var + BN_EPS)
+            with torch.no_grad():
+                B[f"{s.bn}.running_mean"].mul_(1 - BN_MOM).add_(BN_MOM * (mean + P[f"{s.conv}.bias"].detach()))
+                B[f"{s.bn}.running_var"].mul_(1 - BN_MOM).add_(BN_MOM * var * cnt / max(cnt - 1, 1))
+                B[f"{s.bn}.num_batches_tracked"] += 1
         scale = gamma * invstd
         shift = beta - mean * scale
-        with torch.no_grad():
-            B[f"{s.bn}.running_mean"].mul_(1 - BN_MOM).add_(BN_MOM * (mean + P[f"{s.conv}.bias"].detach()))
-            B[f"{s.bn}.running_var"].mul_(1 - BN_MOM).add_(BN_MOM * var * cnt / max(cnt - 1, 1))
-            B[f"{s.bn}.num_batches_tracked"] += 1
         a = pooled = idx = None
         if not defer:
             a_val = _bf(F.relu(yf * scale + shift))
@@ -129,8 +135,15 @@ def emulate_traced_step(m, specs, batch, ignore_index, cin_pad, fault=None):
         yv = _nchw(r["y"].float()).requires_grad_(True)
         g_ = P[f"{s.bn}.weight"].detach().clone().requires_grad_(True)
         b_ = P[f"{s.bn}.bias"].detach().clone().requires_grad_(True)
-        a = F.relu(F.batch_norm(yv, None, None, g_, b_, True, BN_MOM, BN_EPS))
-        a.backward(_nchw(da.float()))
+        if frozen:
+            cb_ = P[f"{s.conv}.bias"].detach().clone().requires_grad_(True)
+            a = F.relu(F.batch_norm(yv + cb_[None, :, None, None], B[f"{s.bn}.running_mean"].detach().clone(),
+                                    B[f"{s.bn}.running_var"].detach().clone(), g_, b_, False, BN_MOM, BN_EPS))
+            a.backward(_nchw(da.float()))
+            grads[f"{s.conv}.bias"].copy_(cb_.grad)
+        else:
+            a = F.relu(F.batch_norm(yv, None, None, g_, b_, True, BN_MOM, BN_EPS))
+            a.backward(_nchw(da.float()))
         dyv = yv.grad
         if fault is not None and fault.startswith(f"bn_bwd_coef_layer{i}:"):
             off = float(fault.split(":")[1])

@@ -278,6 +278,7 @@ class _Schedule:
         # chips/s (+1.3 %), end to end 892 -> 908 (+1.8 %), every overlapped run above every serial one
         # (profiles/r02_wgrad_overlap_ab.md).  Set False for a strictly single-stream backward.
         self.overlap_wgrad = True
+        self.wgrad_after_dgrad = True      # see _layer_backward: launch order of the two tensor kernels of a layer
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._fold_cache: Dict[str, Tuple[tuple, torch.Tensor, torch.Tensor]] = {}
         self.launches = 0  # kernels launched by the last forward/backward (for bench accounting)
@@ -538,14 +539,28 @@ class _Schedule:
                                 grads[f"{s.bn}.weight"], grads[f"{s.bn}.bias"], coef)
         dy = torch.empty((n, hh, ww, s.cout), **bw.bf)
         ops.bn_relu_bwd_apply(da, sv.y, dy, sv.scale, sv.shift, coef)
+        dy_ready = None
         if bw.side is not None:
-            bw.side.wait_stream(bw.main)                      # dy is ready
-            with torch.cuda.stream(bw.side):
-                ops.conv3x3_wgrad(sv.x, dy, grads[f"{s.conv}.weight"], bw.ws, s.cin)
-            dy.record_stream(bw.side)                      # keep dy alive until the side stream is done
-        else:
-            self._timed("wgrad", s, n, hh * ww,
-                        lambda: ops.conv3x3_wgrad(sv.x, dy, grads[f"{s.conv}.weight"], bw.ws, s.cin))
+            dy_ready = torch.cuda.Event()
+            dy_ready.record(bw.main)
+
+        def launch_wgrad():
+            if bw.side is not None:
+                bw.side.wait_event(dy_ready)                  # dy is ready
+                with torch.cuda.stream(bw.side):
+                    ops.conv3x3_wgrad(sv.x, dy, grads[f"{s.conv}.weight"], bw.ws, s.cin)
+                dy.record_stream(bw.side)                  # keep dy alive until the side stream is done
+            else:
+                self._timed("wgrad", s, n, hh * ww,
+                            lambda: ops.conv3x3_wgrad(sv.x, dy, grads[f"{s.conv}.weight"], bw.ws, s.cin))
+
+        # launch ORDER matters when wgrads overlap: two tensor kernels cannot co-reside (one CTA per SM), the
+        # block scheduler serves the kernel that was launched first.  dgrad is on the critical path, so it goes
+        # first; the wgrad's CTAs then run when the main stream is in its next HBM-bound phase (BatchNorm-backward,
+        # pool / upsample backward), whose blocks DO fit beside a wgrad CTA.
+        wgrad_first = bw.side is None or not self.wgrad_after_dgrad
+        if wgrad_first:
+            launch_wgrad()
         bw.launches += 5
         dx = None
         if need_dx:
@@ -571,6 +586,8 @@ class _Schedule:
             else:
                 self._timed("dgrad", s, n, hh * ww, lambda: ops.conv3x3_dgrad(dy, wd, dx))
             bw.launches += 1
+        if not wgrad_first:
+            launch_wgrad()
         self._tr("layer_bwd", spec=s, da=da, y=sv.y, x=sv.x, dy=dy, dx=dx, coef=coef,
                  dw=grads[f"{s.conv}.weight"], dgamma=grads[f"{s.bn}.weight"], dbeta=grads[f"{s.bn}.bias"],
                  fused_reduce=bn_parts is not None)

@@ -557,7 +557,8 @@ class _Schedule:
         # launch ORDER matters when wgrads overlap: two tensor kernels cannot co-reside (one CTA per SM), the
         # block scheduler serves the kernel that was launched first.  dgrad is on the critical path, so it goes
         # first; the wgrad's CTAs then run when the main stream is in its next HBM-bound phase (BatchNorm-backward,
-        # pool / upsample backward), whose blocks DO fit beside a wgrad CTA.
+        # pool / upsample backward), whose blocks DO fit beside a wgrad CTA.  (Measured neutral within noise in the
+        # power-capped step, profiles/r02_wgrad_overlap_ab.md: 881.1 vs 882.4 chips/s; kept for the rationale.)
         wgrad_first = bw.side is None or not self.wgrad_after_dgrad
         if wgrad_first:
             launch_wgrad()

@@ -2,12 +2,11 @@
 # A/B on one box, alternating: launch order of a layer's dgrad / wgrad when wgrads run on the side stream
 mkdir -p gpurun_out
 for rep in 1 2 3; do
-  for ord in 0 1; do
+  for ord in ${ORDERS:-0 1}; do
     FPB200_WGRAD_AFTER_DGRAD=$ord python bench.py --steps 30 --warmup 5 --no-infer --no-cpu-baseline \
         > gpurun_out/r2ac_order${ord}_rep${rep}.json 2> gpurun_out/r2ac_order${ord}_rep${rep}.err
   done
 done
-python bench.py --infer-only > gpurun_out/r2ac_infer_n1.json 2> gpurun_out/r2ac_infer_n1.err
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r2ac_*.json")):

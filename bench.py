@@ -326,8 +326,8 @@ def run_ours(args):
                if world > 1 and not args.no_allreduce else None)
     dp_check = data_parallel_check(model, reducer, dev, rank, world, args) if reducer is not None else None
     engine = model.model._engine
-    if os.environ.get("FPB200_WGRAD_AFTER_DGRAD") in ("0", "1", "2"):   # A/B switch: order of dgrad / wgrad of a layer
-        engine.wgrad_after_dgrad = int(os.environ["FPB200_WGRAD_AFTER_DGRAD"])
+    if os.environ.get("FPB200_WGRAD_AFTER_DGRAD") in ("0", "1"):   # A/B switch: launch order of dgrad / wgrad of a layer
+        engine.wgrad_after_dgrad = os.environ["FPB200_WGRAD_AFTER_DGRAD"] == "1"
     if os.environ.get("FPB200_OVERLAP_WGRAD") in ("0", "1"):   # A/B switch: wgrads on a second stream
         engine.overlap_wgrad = os.environ["FPB200_OVERLAP_WGRAD"] == "1"
 

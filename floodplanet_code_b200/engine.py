@@ -546,12 +546,6 @@ class _Schedule:
 
         def launch_wgrad():
             if bw.side is not None:
-                if self.wgrad_after_dgrad == 2 and need_dx:
-                    # experiment: hold the wgrad back until the layer's dgrad has FINISHED, so that it runs entirely
-                    # beside the HBM-bound passes that follow on the main stream
-                    done = torch.cuda.Event()
-                    done.record(bw.main)
-                    bw.side.wait_event(done)
                 bw.side.wait_event(dy_ready)                  # dy is ready
                 with torch.cuda.stream(bw.side):
                     ops.conv3x3_wgrad(sv.x, dy, grads[f"{s.conv}.weight"], bw.ws, s.cin)

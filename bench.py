@@ -264,8 +264,7 @@ def infer_block(model, dev, rank, world, args):
         t0 = time.perf_counter()
         e0.record()
         info = predict_scene_from_host(unet, scene, crop=crop, tile_batch=args.infer_tile_batch, rank=rank,
-                                       world=world, mask_host=mask_host, device=dev,
-                                       two_lanes=os.environ.get("FPB200_INFER_LANES", "2") != "1")
+                                       world=world, mask_host=mask_host, device=dev)
         e1.record()
         torch.cuda.synchronize(dev)
         ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0)

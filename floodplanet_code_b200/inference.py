@@ -103,16 +103,6 @@ def predict_scene(unet: UNet, scene: torch.Tensor, crop: int = 512, stride: Opti
 _COPY_STREAMS = {}
 
 
-_LANE_STREAMS = {}
-
-
-def _lane_streams(dev):
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
-    if key not in _LANE_STREAMS:
-        _LANE_STREAMS[key] = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    return _LANE_STREAMS[key]
-
-
 def _row_len(tiles, t) -> int:
     """Number of tiles of `tiles` that start on the same scene row as tile t."""
     return sum(1 for u in tiles if u[0] == t[0])
@@ -128,7 +118,7 @@ def _copy_stream(dev) -> "torch.cuda.Stream":
 @torch.no_grad()
 def predict_scene_from_host(unet: UNet, scene_host: torch.Tensor, crop: int = 512, tile_batch: int = 32,
                             rank: int = 0, world: int = 1, mask_host: Optional[torch.Tensor] = None,
-                            device: Optional[torch.device] = None, two_lanes: bool = True):
+                            device: Optional[torch.device] = None):
     """End-to-end form of :func:`predict_scene` for a scene in HOST memory -- the shape of the
     reference loop (infer.py:112-184: `batch[key].to(device)` per batch :117-119, model, D2H :122,
     stitch :160-163, mask :181-184), non-overlapping tiles (infer.py:64-65: stride = crop).
@@ -198,45 +188,21 @@ def predict_scene_from_host(unet: UNet, scene_host: torch.Tensor, crop: int = 51
                 ready[slot].record(copier)
             return c * (e - s0) * W * 4
 
-        # two compute lanes process alternate tile batches: the tensor-bound convolutions of one batch run beside
-        # the HBM-bound kernels (ingest, pooling, upsample, head, softmax-stitch) of the other.  Tiles never overlap
-        # at stride = crop, so both lanes may add into the same canvas.  The second lane starts after the first
-        # batch's kernels are enqueued: packed weights and folded BatchNorm coefficients are then cached, no lane
-        # ever reads a cache entry another lane is still writing.
-        lanes = _lane_streams(dev) if (two_lanes and len(batches) > 1) else [compute]
-        for ln in lanes:
-            if ln is not compute:
-                ln.wait_stream(compute)                      # canvas / weight are zeroed on the caller's stream
-        first_enqueued = None
         h2d += stage(0)
         for i, chunk in enumerate(batches):
             if i + 1 < len(batches):
                 h2d += stage(i + 1)
             slot = i % len(bufs)
             s0, e = spans[i]
-            lane = lanes[i % len(lanes)]
-            with torch.cuda.stream(lane):
-                if i == 1 and first_enqueued is not None:
-                    lane.wait_event(first_enqueued)
-                lane.wait_event(ready[slot])
-                meta_in = [[h0 - s0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
-                x = ops.ingest_scene_tiles(band_view(i), torch.tensor(meta_in, dtype=torch.int32, device=dev),
-                                           crop, crop, engine.cin_pad)
-                consumed[slot].record(lane)                   # the band buffer may be overwritten from here on
-                logits, _ = engine.forward(None, params, buffers, training=False, save=False, ingested=x)
-                meta_out = [[h0 - r0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
-                ops.softmax_stitch_add(logits, canvas, weight, torch.tensor(meta_out, dtype=torch.int32, device=dev))
-                if i == 0 and len(lanes) > 1:
-                    first_enqueued = torch.cuda.Event()
-                    first_enqueued.record(lane)
+            compute.wait_event(ready[slot])
+            meta_in = [[h0 - s0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
+            x = ops.ingest_scene_tiles(band_view(i), torch.tensor(meta_in, dtype=torch.int32, device=dev),
+                                       crop, crop, engine.cin_pad)
+            consumed[slot].record(compute)                    # the band buffer may be overwritten from here on
+            logits, _ = engine.forward(None, params, buffers, training=False, save=False, ingested=x)
+            meta_out = [[h0 - r0, w0, min(hh, H - h0), min(ww, W - w0)] for h0, w0, hh, ww in chunk]
+            ops.softmax_stitch_add(logits, canvas, weight, torch.tensor(meta_out, dtype=torch.int32, device=dev))
             launches += engine.launches + 2
-        for ln in lanes:
-            if ln is not compute:
-                compute.wait_stream(ln)
-                canvas.record_stream(ln)
-                weight.record_stream(ln)
-                for buf in bufs:
-                    buf.record_stream(ln)
         for buf in bufs:
             buf.record_stream(copier)
         # pixels of the band no tile of THIS rank covers keep weight 0 -> canvas 0 -> argmax 0 -> mask 0

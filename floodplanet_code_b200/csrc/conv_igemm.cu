@@ -40,6 +40,7 @@
 //   * BatchNorm batch-statistic partials: per-channel sum / sum of squares of the stored bf16
 //     values, read back conflict-free from the staging tile, accumulated in registers across
 //     all patches of the persistent CTA.
+#include <stdlib.h>
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -64,6 +65,21 @@ struct HaloParams {
 };
 
 constexpr int kPatch = 16;        // patch edge in pixels
+
+// buf / op are compile-time constants after the issue loop is unrolled: the switch folds to one instruction
+__device__ __forceinline__ void umma_bf16_ws_sel(int buf, int op, uint32_t d, uint64_t a, uint64_t b, uint32_t idesc,
+                                                 uint32_t acc) {
+  switch (buf * 3 + op) {
+    case 0: umma_bf16_ws<0, 0>(d, a, b, idesc, acc); break;
+    case 2: umma_bf16_ws<0, 2>(d, a, b, idesc, acc); break;
+    case 3: umma_bf16_ws<1, 0>(d, a, b, idesc, acc); break;
+    case 5: umma_bf16_ws<1, 2>(d, a, b, idesc, acc); break;
+    case 6: umma_bf16_ws<2, 0>(d, a, b, idesc, acc); break;
+    case 8: umma_bf16_ws<2, 2>(d, a, b, idesc, acc); break;
+    case 9: umma_bf16_ws<3, 0>(d, a, b, idesc, acc); break;
+    default: umma_bf16_ws<3, 2>(d, a, b, idesc, acc); break;
+  }
+}
 
 // TAPS = 9: 3x3 / pad 1 (box = patch + 1-pixel halo); TAPS = 1: pointwise (1x1) convolution,
 // the same pipeline with a halo-free 16 x 16 box and a single "tap".
@@ -100,7 +116,9 @@ struct HaloCfg {
   static_assert(4 * BN <= 512, "TMEM: 2 tiles x 2 stages x BN columns");
 };
 
-template <int BN, int KCH, int TAPS, int EW = (BN >= 128 ? 4 : 8)>
+// WS: weight-stationary MMA issue (see the MMA issuer below); a template parameter because the issue loop is one
+// lane's dependent instruction chain -- a runtime switch inside it cost every kernel 25 % (measured).
+template <int BN, int KCH, int TAPS, int EW = (BN >= 128 ? 4 : 8), bool WS = false>
 __global__ void __launch_bounds__(HaloCfg<BN, KCH, TAPS, EW>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYL,
@@ -199,6 +217,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // The whole warp walks the loop with warp-uniform values (so addresses/descriptors live in
     // uniform registers); only the tcgen05 instructions are issued by one elected lane.
     const bool leader = elect_one();
+    // Weight-stationary issue: both 128-row tiles of the patch multiply the same weight slice, so tile 0 issues
+    // tcgen05.mma.ws with collector::b<k>::fill (K slice k of the tap parks in collector buffer k) and tile 1 with
+    // ::lastuse -- the 2 KB (BN = 64) slice is read from shared memory once per tap instead of twice.  An
+    // M128 x N64 x K16 MMA needs 6 KB of operands per 32 tensor cycles against 128 B/clk of shared-memory operand
+    // bandwidth: 48.0 cycles per MMA measured for the plain form (50.2 with the tap-shifted descriptors), 43.5 with
+    // the collector (scripts/umma_ws_microbench.cu, profiles/r03_umma_ws_microbench.txt).
+    static_assert(!WS || KCH / 16 <= 4, "one collector buffer per K slice");
     {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -227,10 +252,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int k = 0; k < KCH / 16; ++k) {
                 // tap shift (r, s), tile half t and K slice k are compile-time byte offsets
                 const uint32_t a_off = (uint32_t(r * kBox + t * 8 + s) * kRB + k * 32) >> 4;
-                if (leader)
-                  umma_bf16(d_tmem + t * BN, smem_desc_join(a_lo + a_off, kAHi),
-                            smem_desc_join(b_lo + ((k * 32) >> 4), kBHi), kIdesc,
-                            (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u);
+                const uint32_t acc = (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u;
+                if (leader) {
+                  if constexpr (WS)
+                    umma_bf16_ws_sel(k, t == 0 ? 0 : 2, d_tmem + t * BN, smem_desc_join(a_lo + a_off, kAHi),
+                                     smem_desc_join(b_lo + ((k * 32) >> 4), kBHi), kIdesc, acc);
+                  else
+                    umma_bf16(d_tmem + t * BN, smem_desc_join(a_lo + a_off, kAHi),
+                              smem_desc_join(b_lo + ((k * 32) >> 4), kBHi), kIdesc, acc);
+                }
               }
             }
             if (leader) umma_commit(bempty(sb));
@@ -446,11 +476,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int KCH, int TAPS, int EW = (BN >= 128 ? 4 : 8)>
+// FPB200_HALO_WS (experiment switch, read once): bit 0 = weight-stationary MMAs in the 64 -> 64 / 128 -> 64 channel
+// kernel (default on).
+static int halo_ws_mask() {
+  static const int mask = [] {
+    const char* e = getenv("FPB200_HALO_WS");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return mask;
+}
+
+template <int BN, int KCH, int TAPS, int EW = (BN >= 128 ? 4 : 8), bool WS = false>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                        const CUtensorMap& tmYL, const HaloParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, KCH, TAPS, EW>;
-  auto kern = conv3x3_halo_kernel<BN, KCH, TAPS, EW>;
+  auto kern = conv3x3_halo_kernel<BN, KCH, TAPS, EW, WS>;
   static bool attr_set[kMaxDevices] = {false};   // cudaFuncSetAttribute is per device
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
@@ -526,6 +566,8 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
   // epilogue gains (128 -> 128: 0.834 -> 0.853 ms), and a plain dgrad epilogue has slack either way.
   if (BN == 128 && KCH == 64 && taps == 9 && Cin == 64 && (p.stats_mode != 0 || scale != nullptr))
     return launch_halo<128, 64, 9, 8>(tmA, tmB, tmY, tmYL, p, stream);
+  if (BN == 64 && KCH == 64 && taps == 9 && (halo_ws_mask() & 1))
+    return launch_halo<64, 64, 9, 8, true>(tmA, tmB, tmY, tmYL, p, stream);
 #define FP_HALO_CASE(bn, kch, tp) \
   if (BN == bn && KCH == kch && taps == tp) return launch_halo<bn, kch, tp>(tmA, tmB, tmY, tmYL, p, stream);
   FP_HALO_CASE(128, 64, 9)

@@ -158,6 +158,32 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Weight-stationary form: the B operand of an MMA issued with collector::bBUF::fill stays in collector buffer BUF
+// (b0..b3) and a later MMA issued with ::use / ::lastuse on the same buffer multiplies a DIFFERENT A (and accumulator)
+// with it without re-reading B from shared memory.  For M = 128 the accumulator layout equals the plain form's
+// (lane = row; scripts/umma_ws_microbench.cu checks it bit for bit).  OP: 0 fill, 1 use, 2 lastuse.
+template <int BUF, int OP>
+__device__ __forceinline__ void umma_bf16_ws(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+  static_assert(BUF >= 0 && BUF < 4 && OP >= 0 && OP < 3, "collector buffer b0..b3, fill / use / lastuse");
+#define FP_WS_ASM(QUAL)                                                                               \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                    \
+               "tcgen05.mma.ws.cta_group::1.kind::f16.collector::" QUAL " [%0], %1, %2, %3, p;\n\t}\n" \
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory")
+  if constexpr (BUF == 0 && OP == 0) FP_WS_ASM("b0::fill");
+  else if constexpr (BUF == 0 && OP == 1) FP_WS_ASM("b0::use");
+  else if constexpr (BUF == 0 && OP == 2) FP_WS_ASM("b0::lastuse");
+  else if constexpr (BUF == 1 && OP == 0) FP_WS_ASM("b1::fill");
+  else if constexpr (BUF == 1 && OP == 1) FP_WS_ASM("b1::use");
+  else if constexpr (BUF == 1 && OP == 2) FP_WS_ASM("b1::lastuse");
+  else if constexpr (BUF == 2 && OP == 0) FP_WS_ASM("b2::fill");
+  else if constexpr (BUF == 2 && OP == 1) FP_WS_ASM("b2::use");
+  else if constexpr (BUF == 2 && OP == 2) FP_WS_ASM("b2::lastuse");
+  else if constexpr (BUF == 3 && OP == 0) FP_WS_ASM("b3::fill");
+  else if constexpr (BUF == 3 && OP == 1) FP_WS_ASM("b3::use");
+  else FP_WS_ASM("b3::lastuse");
+#undef FP_WS_ASM
+}
 // Arrives (count 1) on the mbarrier once all previously issued MMAs retire.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

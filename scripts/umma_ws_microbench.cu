@@ -1,0 +1,470 @@
+// Microbenchmark + functional check of the WEIGHT-STATIONARY form of tcgen05.mma on B200:
+//   tcgen05.mma.ws.cta_group::1.kind::f16.collector::bN::{fill,use,lastuse}
+// The halo convolution with 64 output channels issues M128 x N64 x K16 MMAs whose operands (A 4 KB + B 2 KB per
+// 32 tensor cycles) exceed the 128 B/clk shared-memory operand path (scripts/umma_microbench.cu: 48 cycles / MMA).
+// Both 128-row tiles of a patch multiply the SAME weight slice, so a B operand kept in one of the four collector
+// buffers b0..b3 need not be re-read.  This program measures (1) cycles per MMA for the plain form, the .ws form without
+// reuse, and .ws with each B slice used by 2 or 4 consecutive tile MMAs, in the issue order of the conv kernel;
+// (2) that the accumulator layout of .ws M = 128 equals the plain form's (lane = row), bit for bit, on integer data.
+//
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I floodplanet_code_b200/csrc \
+//        scripts/umma_ws_microbench.cu -o gpurun_out/umma_ws_microbench && gpurun_out/umma_ws_microbench
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+#include "ptx.cuh"
+
+using namespace fp;
+
+#define WS_MMA(NAME, QUAL)                                                                                     \
+  __device__ __forceinline__ void NAME(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {     \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                             \
+                 "tcgen05.mma" QUAL " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) \
+                 : "memory");                                                                                  \
+  }
+WS_MMA(mma_ws, ".ws.cta_group::1.kind::f16")
+WS_MMA(mma_ws_fill0, ".ws.cta_group::1.kind::f16.collector::b0::fill")
+WS_MMA(mma_ws_fill1, ".ws.cta_group::1.kind::f16.collector::b1::fill")
+WS_MMA(mma_ws_fill2, ".ws.cta_group::1.kind::f16.collector::b2::fill")
+WS_MMA(mma_ws_fill3, ".ws.cta_group::1.kind::f16.collector::b3::fill")
+WS_MMA(mma_ws_use0, ".ws.cta_group::1.kind::f16.collector::b0::use")
+WS_MMA(mma_ws_use1, ".ws.cta_group::1.kind::f16.collector::b1::use")
+WS_MMA(mma_ws_use2, ".ws.cta_group::1.kind::f16.collector::b2::use")
+WS_MMA(mma_ws_use3, ".ws.cta_group::1.kind::f16.collector::b3::use")
+WS_MMA(mma_ws_last0, ".ws.cta_group::1.kind::f16.collector::b0::lastuse")
+WS_MMA(mma_ws_last1, ".ws.cta_group::1.kind::f16.collector::b1::lastuse")
+WS_MMA(mma_ws_last2, ".ws.cta_group::1.kind::f16.collector::b2::lastuse")
+WS_MMA(mma_ws_last3, ".ws.cta_group::1.kind::f16.collector::b3::lastuse")
+WS_MMA(mma_a_fill, ".cta_group::1.kind::f16.collector::a::fill")
+WS_MMA(mma_a_use, ".cta_group::1.kind::f16.collector::a::use")
+WS_MMA(mma_a_last, ".cta_group::1.kind::f16.collector::a::lastuse")
+
+// op: 0 fill, 1 use, 2 lastuse; buf 0..3 (compile-time after unrolling)
+__device__ __forceinline__ void mma_ws_coll(int buf, int op, uint32_t d, uint64_t a, uint64_t b, uint32_t idesc,
+                                            uint32_t acc) {
+  switch (buf * 3 + op) {
+    case 0: mma_ws_fill0(d, a, b, idesc, acc); break;
+    case 1: mma_ws_use0(d, a, b, idesc, acc); break;
+    case 2: mma_ws_last0(d, a, b, idesc, acc); break;
+    case 3: mma_ws_fill1(d, a, b, idesc, acc); break;
+    case 4: mma_ws_use1(d, a, b, idesc, acc); break;
+    case 5: mma_ws_last1(d, a, b, idesc, acc); break;
+    case 6: mma_ws_fill2(d, a, b, idesc, acc); break;
+    case 7: mma_ws_use2(d, a, b, idesc, acc); break;
+    case 8: mma_ws_last2(d, a, b, idesc, acc); break;
+    case 9: mma_ws_fill3(d, a, b, idesc, acc); break;
+    case 10: mma_ws_use3(d, a, b, idesc, acc); break;
+    default: mma_ws_last3(d, a, b, idesc, acc); break;
+  }
+}
+
+enum Mode { PLAIN = 0, WS_PLAIN = 1, WS_REUSE = 2, WS_REUSE_ONEBUF = 3, A_COLLECT = 4 };
+
+constexpr int kABytes = 80 * 1024;   // a (16+2) x (32+2) halo box of 128-byte rows = 78336 B
+constexpr int kBBytes = 256 * 128;
+
+// TILES consecutive 128-row tiles share each B slice.  Issue order as in the conv kernel: per tap, per tile, per K slice.
+template <int N, int MODE, int TILES>
+__global__ void __launch_bounds__(128, 1) ws_bench(int iters, long long* out_cycles, int* out_count) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + kABytes;
+  const uint32_t bar = base + kABytes + kBBytes, slot = bar + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t o = threadIdx.x * 16; o < kABytes + kBBytes; o += blockDim.x * 16)
+    st_shared_v4(base + o, make_uint4(0, 0, 0, 0));
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, N, 0, 0);
+  constexpr uint32_t kRB = 128;
+  constexpr int kBoxW = TILES == 4 ? 34 : 18;    // tile t covers box columns [8t, 8t+8) (+ tap shift)
+  long long t0 = 0, t1 = 0;
+  int count = 0;
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const uint32_t b_lo = smem_desc_lo(b_base, 16);
+    constexpr uint32_t kBHi = smem_desc_hi(8 * kRB, 128);
+    constexpr uint32_t kAHiBox = smem_desc_hi(kBoxW * kRB, 128);
+    const uint32_t a_lo = smem_desc_lo(a_base, 16);
+    __syncwarp();
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int r = tap / 3, s = tap - 3 * r;
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (it | tap) != 0 ? 1u : (k != 0 ? 1u : 0u);
+            const uint32_t d = tmem + t * N;
+            const uint32_t a_off = (uint32_t(r * kBoxW + t * 8 + s) * kRB + k * 32) >> 4;
+            const uint64_t da = smem_desc_join(a_lo + a_off, kAHiBox);
+            const uint64_t db = smem_desc_join(b_lo + ((tap * 4 + k) * 32 >> 4) % 64 + 0, kBHi);
+            if (leader) {
+              if (MODE == PLAIN) umma_bf16(d, da, db, kIdesc, acc);
+              else if (MODE == WS_PLAIN) mma_ws(d, da, db, kIdesc, acc);
+              else if (MODE == WS_REUSE) mma_ws_coll(k, t == 0 ? 0 : (t == TILES - 1 ? 2 : 1), d, da, db, kIdesc, acc);
+              else if (MODE == A_COLLECT) {   // same A for all 4 K slices?  no: here A reuse needs equal A, shown for reference
+                const uint64_t da0 = smem_desc_join(a_lo + ((uint32_t(r * kBoxW + s) * kRB) >> 4), kAHiBox);
+                if (t == 0 && k == 0) mma_a_fill(d, da0, db, kIdesc, acc);
+                else if (t == TILES - 1 && k == 3) mma_a_last(d, da0, db, kIdesc, acc);
+                else mma_a_use(d, da0, db, kIdesc, acc);
+              }
+            }
+            ++count;
+          }
+        }
+      }
+    }
+    if (leader) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    t1 = clock64();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+    if (lane == 0 && blockIdx.x == 0) { *out_cycles = t1 - t0; *out_count = count; }
+  }
+}
+
+// K-slice-major order inside a tap (per tap, per K slice, per tile): the B slice is used by TILES back-to-back MMAs,
+// one collector buffer suffices
+template <int N, int TILES>
+__global__ void __launch_bounds__(128, 1) ws_bench_kmajor(int iters, long long* out_cycles, int* out_count) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + kABytes;
+  const uint32_t bar = base + kABytes + kBBytes, slot = bar + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t o = threadIdx.x * 16; o < kABytes + kBBytes; o += blockDim.x * 16)
+    st_shared_v4(base + o, make_uint4(0, 0, 0, 0));
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, N, 0, 0);
+  constexpr uint32_t kRB = 128;
+  constexpr int kBoxW = TILES == 4 ? 34 : 18;
+  long long t0 = 0, t1 = 0;
+  int count = 0;
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const uint32_t b_lo = smem_desc_lo(b_base, 16);
+    constexpr uint32_t kBHi = smem_desc_hi(8 * kRB, 128);
+    constexpr uint32_t kAHiBox = smem_desc_hi(kBoxW * kRB, 128);
+    const uint32_t a_lo = smem_desc_lo(a_base, 16);
+    __syncwarp();
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int r = tap / 3, s = tap - 3 * r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+            const uint32_t acc = (it | tap) != 0 ? 1u : (k != 0 ? 1u : 0u);
+            const uint32_t d = tmem + t * N;
+            const uint32_t a_off = (uint32_t(r * kBoxW + t * 8 + s) * kRB + k * 32) >> 4;
+            const uint64_t da = smem_desc_join(a_lo + a_off, kAHiBox);
+            const uint64_t db = smem_desc_join(b_lo + ((tap * 4 + k) * 32 >> 4) % 64, kBHi);
+            if (leader) mma_ws_coll((tap * 4 + k) & 3, t == 0 ? 0 : (t == TILES - 1 ? 2 : 1), d, da, db, kIdesc, acc);
+            ++count;
+          }
+        }
+      }
+    }
+    if (leader) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    t1 = clock64();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+    if (lane == 0 && blockIdx.x == 0) { *out_cycles = t1 - t0; *out_count = count; }
+  }
+}
+
+
+// The conv kernel's MMA stream does not run alone: per 72 MMAs (one 64-channel K chunk of a patch) the TMA unit writes a
+// 41.5 KB activation box and 9 x 8 KB weight tiles into shared memory.  This variant runs the same MMA stream while
+// warp 1 keeps DEPTH bulk copies (global -> shared, 8 KB each, L2-resident source) in flight into a separate region and
+// reports the fill bytes per MMA next to the cycles per MMA: does shared-memory WRITE traffic share the 128 B/clk?
+template <int MODE, int DEPTH>
+__global__ void __launch_bounds__(128, 1) ws_bench_fill(int iters, const uint8_t* __restrict__ src, long long* out_cycles,
+                                                         int* out_count, long long* out_fill) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int N = 64, TILES = 2;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_base = base, b_base = base + kABytes, f_base = b_base + kBBytes;
+  const uint32_t bar = f_base + 4 * 8192, slot = bar + 8, fbar = bar + 16;   // fbar[4]
+  volatile int* done = reinterpret_cast<volatile int*>(al + kABytes + kBBytes + 4 * 8192 + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t o = threadIdx.x * 16; o < kABytes + kBBytes + 4 * 8192; o += blockDim.x * 16)
+    st_shared_v4(base + o, make_uint4(0, 0, 0, 0));
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(fbar + 8 * i, 1);
+    fence_barrier_init();
+    *done = 0;
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(al + kABytes + kBBytes + 4 * 8192 + 8);
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, N, 0, 0);
+  constexpr uint32_t kRB = 128;
+  constexpr int kBoxW = 18;
+  if (warp == 0) {
+    long long t0 = 0, t1 = 0;
+    int count = 0;
+    const bool leader = elect_one();
+    const uint32_t b_lo = smem_desc_lo(b_base, 16);
+    constexpr uint32_t kBHi = smem_desc_hi(8 * kRB, 128);
+    constexpr uint32_t kAHiBox = smem_desc_hi(kBoxW * kRB, 128);
+    const uint32_t a_lo = smem_desc_lo(a_base, 16);
+    __syncwarp();
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int r = tap / 3, s = tap - 3 * r;
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (it | tap) != 0 ? 1u : (k != 0 ? 1u : 0u);
+            const uint32_t d = tmem + t * N;
+            const uint32_t a_off = (uint32_t(r * kBoxW + t * 8 + s) * kRB + k * 32) >> 4;
+            const uint64_t da = smem_desc_join(a_lo + a_off, kAHiBox);
+            const uint64_t db = smem_desc_join(b_lo + ((tap * 4 + k) * 32 >> 4) % 64, kBHi);
+            if (leader) {
+              if (MODE == PLAIN) umma_bf16(d, da, db, kIdesc, acc);
+              else mma_ws_coll(k, t == 0 ? 0 : 2, d, da, db, kIdesc, acc);
+            }
+            ++count;
+          }
+        }
+      }
+    }
+    if (leader) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    t1 = clock64();
+    tc_fence_after();
+    *done = 1;
+    if (lane == 0 && blockIdx.x == 0) { *out_cycles = t1 - t0; *out_count = count; }
+  } else if (warp == 1 && lane == 0 && DEPTH > 0) {
+    long long chunks = 0;
+    uint32_t phase = 0;
+    // prime DEPTH copies, then re-issue each slot as soon as it lands
+    for (int i = 0; i < DEPTH; ++i) {
+      mbar_arrive_expect_tx(fbar + 8 * i, 8192);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       f_base + i * 8192), "l"(src + ((blockIdx.x * 4 + i) % 128) * 8192), "r"(8192), "r"(fbar + 8 * i) : "memory");
+    }
+    while (!*done) {
+      for (int i = 0; i < DEPTH; ++i) {
+        mbar_wait(fbar + 8 * i, phase);
+        ++chunks;
+        mbar_arrive_expect_tx(fbar + 8 * i, 8192);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         f_base + i * 8192), "l"(src + ((blockIdx.x * 4 + i + chunks) % 128) * 8192), "r"(8192), "r"(fbar + 8 * i) : "memory");
+      }
+      phase ^= 1u;
+    }
+    for (int i = 0; i < DEPTH; ++i) mbar_wait(fbar + 8 * i, phase);   // drain before the CTA exits
+    if (blockIdx.x == 0) *out_fill = chunks * 8192;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <typename K>
+static void run_fill(K kern, const char* name, int depth, int iters, int grid, const uint8_t* src) {
+  long long *d_cyc, *d_fill; int* d_cnt;
+  cudaMalloc(&d_cyc, 8); cudaMalloc(&d_cnt, 4); cudaMalloc(&d_fill, 8);
+  cudaMemset(d_fill, 0, 8);
+  const int smem = kABytes + kBBytes + 4 * 8192 + 2048;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  kern<<<grid, 128, smem>>>(8, src, d_cyc, d_cnt, d_fill);
+  kern<<<grid, 128, smem>>>(iters, src, d_cyc, d_cnt, d_fill);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0, fill = 0; int cnt = 0;
+  cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&fill, d_fill, 8, cudaMemcpyDeviceToHost);
+  const double per = cnt ? (double)cyc / cnt : 0.0;
+  printf("%-22s copies in flight %d grid=%3d  %7.1f cycles/MMA   fill %6.2f KB/MMA (%5.1f B/clk)   tensor-pipe bound %5.1f %%   %s\n",
+         name, depth, grid, per, cnt ? fill / 1024.0 / cnt : 0.0, cyc ? (double)fill / cyc : 0.0, 100.0 * 32.0 / per,
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d_cyc); cudaFree(d_cnt); cudaFree(d_fill);
+}
+
+template <typename K>
+static void run_kernel(K kern, const char* name, int N, int tiles, int iters, int grid) {
+  long long* d_cyc; int* d_cnt;
+  cudaMalloc(&d_cyc, 8); cudaMalloc(&d_cnt, 4);
+  const int smem = kABytes + kBBytes + 2048;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  kern<<<grid, 128, smem>>>(8, d_cyc, d_cnt);
+  kern<<<grid, 128, smem>>>(iters, d_cyc, d_cnt);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0; int cnt = 0;
+  cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+  const double per = cnt ? (double)cyc / cnt : 0.0;
+  const double floor_c = 128.0 * N / 256.0;
+  printf("%-44s N=%3d tiles=%d grid=%3d  %7.1f cycles/MMA   floor %4.0f   tensor-pipe bound %5.1f %%   %s\n", name, N, tiles,
+         grid, per, floor_c, 100.0 * floor_c / per, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d_cyc); cudaFree(d_cnt);
+}
+
+// ------------------------------------------------------------------------------------------------ functional check
+// One 128 x 64 x 64 product (4 K slices), A and B written to shared memory in the 128-byte-swizzled K-major layout the conv
+// kernel uses, accumulator read back with tcgen05.ld 32x32b: out[row][col] for the plain and the .ws form.
+template <int WS>
+__global__ void __launch_bounds__(128, 1) ws_func(const __nv_bfloat16* A, const __nv_bfloat16* B, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_base = base, b_base = base + 16384, bar = base + 16384 + 8192, slot = bar + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // row i (128 bytes = 64 bf16 of K), 16-byte chunk c stored at chunk position c ^ (i & 7)
+  for (int e = threadIdx.x; e < 128 * 64; e += 128) {
+    const int i = e >> 6, kk = e & 63, c = kk >> 3, w = kk & 7;
+    reinterpret_cast<__nv_bfloat16*>(al + i * 128 + ((c ^ (i & 7)) << 4))[w] = A[e];
+  }
+  for (int e = threadIdx.x; e < 64 * 64; e += 128) {
+    const int i = e >> 6, kk = e & 63, c = kk >> 3, w = kk & 7;
+    reinterpret_cast<__nv_bfloat16*>(al + 16384 + i * 128 + ((c ^ (i & 7)) << 4))[w] = B[e];
+  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(slot, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(al + 16384 + 8192 + 16);
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, 64, 0, 0);
+  if (warp == 0) {
+    const bool leader = elect_one();
+    constexpr uint32_t kHi = smem_desc_hi(1024, 128);
+    const uint32_t a_lo = smem_desc_lo(a_base, 16), b_lo = smem_desc_lo(b_base, 16);
+#pragma unroll
+    for (int t = 0; t < 2; ++t)      // two "tiles" (the same A, two accumulators) so that fill / lastuse are both exercised
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t da = smem_desc_join(a_lo + (k * 32 >> 4), kHi), db = smem_desc_join(b_lo + (k * 32 >> 4), kHi);
+        if (leader) {
+          if (WS) mma_ws_coll(k, t == 0 ? 0 : 2, tmem + t * 64, da, db, kIdesc, k != 0);
+          else umma_bf16(tmem + t * 64, da, db, kIdesc, k != 0);
+        }
+      }
+    if (leader) umma_commit(bar);
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int t = 0; t < 2; ++t)
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem + (uint32_t(warp * 32) << 16) + t * 64 + h * 32, r);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) out[(t * 128 + warp * 32 + lane) * 64 + h * 32 + j] = __uint_as_float(r[j]);
+    }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+static int functional() {
+  std::vector<__nv_bfloat16> A(128 * 64), B(64 * 64);
+  std::vector<float> Af(128 * 64), Bf(64 * 64), ref(128 * 64, 0.f);
+  for (int i = 0; i < 128; ++i) for (int k = 0; k < 64; ++k) { Af[i * 64 + k] = float((i * 3 + k * 5) % 7 - 3); A[i * 64 + k] = __float2bfloat16(Af[i * 64 + k]); }
+  for (int n = 0; n < 64; ++n) for (int k = 0; k < 64; ++k) { Bf[n * 64 + k] = float((n * 2 + k * 3 + (n * k) % 5) % 5 - 2); B[n * 64 + k] = __float2bfloat16(Bf[n * 64 + k]); }
+  for (int i = 0; i < 128; ++i) for (int n = 0; n < 64; ++n) { float s = 0; for (int k = 0; k < 64; ++k) s += Af[i * 64 + k] * Bf[n * 64 + k]; ref[i * 64 + n] = s; }
+  __nv_bfloat16 *dA, *dB; float* dO;
+  cudaMalloc(&dA, A.size() * 2); cudaMalloc(&dB, B.size() * 2); cudaMalloc(&dO, 2 * 128 * 64 * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice);
+  int bad_total = 0;
+  for (int ws = 0; ws < 2; ++ws) {
+    cudaMemset(dO, 0xff, 2 * 128 * 64 * 4);
+    const int smem = 16384 + 8192 + 2048;
+    if (ws) ws_func<1><<<1, 128, smem>>>(dA, dB, dO); else ws_func<0><<<1, 128, smem>>>(dA, dB, dO);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<float> out(2 * 128 * 64);
+    cudaMemcpy(out.data(), dO, out.size() * 4, cudaMemcpyDeviceToHost);
+    int bad = 0, first = -1;
+    for (int t = 0; t < 2; ++t) for (int i = 0; i < 128 * 64; ++i) if (out[t * 128 * 64 + i] != ref[i]) { if (first < 0) first = t * 128 * 64 + i; ++bad; }
+    printf("functional %-6s: %s, %d of %d accumulator elements differ from the integer reference%s\n", ws ? ".ws" : "plain",
+           e == cudaSuccess ? "ok" : cudaGetErrorString(e), bad, 2 * 128 * 64, bad ? " (layout differs?)" : "");
+    if (bad) {
+      printf("  first mismatch at tile %d row %d col %d: got %g want %g\n", first / 8192, (first % 8192) / 64, first % 64, out[first], ref[first % 8192]);
+      // where does row 0 / row 1 / row 64 of the reference sit in the dump?
+      for (int want : {0, 1, 32, 64}) for (int i = 0; i < 128; ++i) { bool eq = true; for (int n = 0; n < 64 && eq; ++n) eq = out[i * 64 + n] == ref[want * 64 + n]; if (eq) printf("  reference row %d found at dumped row %d\n", want, i); }
+    }
+    bad_total += bad;
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dO);
+  return bad_total;
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  printf("%s, %d SMs, SM clock %d MHz; one op = one M128 x N x K16 bf16 MMA, A = tap-shifted halo-box rows, clock64 around "
+         "36 x tiles ops x iters issued by one thread\n", p.name, p.multiProcessorCount, p.clockRate / 1000);
+  functional();
+  const int it = 200;
+  {
+    uint8_t* src; cudaMalloc(&src, 128 * 8192 + 8192); cudaMemset(src, 0, 128 * 8192 + 8192);
+    printf("-- MMA stream (N = 64, 2 tiles, tap-shifted A) with concurrent bulk copies into shared memory (conv kernel: 1.57 KB/MMA)\n");
+    for (int grid : {1, 148}) {
+      run_fill(ws_bench_fill<PLAIN, 0>, "plain SS", 0, it, grid, src);
+      run_fill(ws_bench_fill<PLAIN, 1>, "plain SS", 1, it, grid, src);
+      run_fill(ws_bench_fill<PLAIN, 2>, "plain SS", 2, it, grid, src);
+      run_fill(ws_bench_fill<PLAIN, 4>, "plain SS", 4, it, grid, src);
+      run_fill(ws_bench_fill<WS_REUSE, 0>, ".ws fill / lastuse", 0, it, grid, src);
+      run_fill(ws_bench_fill<WS_REUSE, 1>, ".ws fill / lastuse", 1, it, grid, src);
+      run_fill(ws_bench_fill<WS_REUSE, 2>, ".ws fill / lastuse", 2, it, grid, src);
+      run_fill(ws_bench_fill<WS_REUSE, 4>, ".ws fill / lastuse", 4, it, grid, src);
+    }
+    cudaFree(src);
+  }
+  for (int grid : {1, 148}) {
+    run_kernel(ws_bench<64, PLAIN, 2>, "plain SS", 64, 2, it, grid);
+    run_kernel(ws_bench<64, WS_PLAIN, 2>, ".ws, no collector qualifier", 64, 2, it, grid);
+    run_kernel(ws_bench<64, WS_REUSE, 2>, ".ws, b0-b3 fill (tile 0) / lastuse (tile 1)", 64, 2, it, grid);
+    run_kernel(ws_bench<64, WS_REUSE, 4>, ".ws, b0-b3 fill / use / use / lastuse", 64, 4, it, grid);
+    run_kernel(ws_bench_kmajor<64, 2>, ".ws, K-slice-major, fill / lastuse", 64, 2, it, grid);
+    run_kernel(ws_bench_kmajor<64, 4>, ".ws, K-slice-major, fill / use x2 / lastuse", 64, 4, it, grid);
+    run_kernel(ws_bench<64, A_COLLECT, 2>, "plain, A collector (same A, 8 uses)", 64, 2, it, grid);
+    run_kernel(ws_bench<128, PLAIN, 2>, "plain SS", 128, 2, it, grid);
+    run_kernel(ws_bench<128, WS_PLAIN, 2>, ".ws, no collector qualifier", 128, 2, it, grid);
+    run_kernel(ws_bench<128, WS_REUSE, 2>, ".ws, b0-b3 fill / lastuse", 128, 2, it, grid);
+  }
+  return 0;
+}

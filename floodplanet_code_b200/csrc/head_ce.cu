@@ -132,6 +132,7 @@ head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const float* _
 // ---------------------------------------------------------------------------
 constexpr int kHeadBwdThreads = 256;
 constexpr int kHeadBwdPx = 16;   // pixels per warp iteration (4 per quad lane; 8 spills at 128 registers)
+constexpr int kHeadBwdStages = 2;  // cp.async ring of x vectors per warp: this iteration + the next
 
 template <int NC, bool FUSED>
 __global__ void __launch_bounds__(kHeadBwdThreads, 2)
@@ -142,19 +143,26 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
                    const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
                    float* __restrict__ bn_partials) {
   __shared__ float sw[NC * kHeadC];
-  __shared__ float red[(kHeadBwdThreads / 32) * NC * (kHeadC + 1)];
+  // the cp.async ring of the main loop and the block-reduction scratch of the tail share one allocation
+  constexpr int kRingBytes = (kHeadBwdThreads / 32) * kHeadBwdStages * kHeadBwdPx * 8 * 16;
+  constexpr int kRedBytes = (kHeadBwdThreads / 32) * NC * (kHeadC + 1) * 4;
+  __shared__ __align__(16) uint8_t pool[kRingBytes > kRedBytes ? kRingBytes : kRedBytes];
+  float* red = reinterpret_cast<float*>(pool);
+  uint4* xs = reinterpret_cast<uint4*>(pool);
   for (int i = threadIdx.x; i < NC * kHeadC; i += blockDim.x) sw[i] = i < ncls * kHeadC ? w[i] : 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3;  // which pixel of a quad
   const int cg = lane & 7;    // channel group: channels cg*8 .. cg*8+7
-  float dw[NC][8];
+  // accumulators and per-pixel values are kept as fp32 PAIRS: the kernel is issue bound (~150 instructions per
+  // 8-channel pixel slice, half of them FMAs), and FFMA2 / FADD2 do two of them per issue slot with the same bits
+  float2 dw[NC][4];
   float db[NC];
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
     db[k] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dw[k][j] = 0.f;
+    for (int j = 0; j < 4; ++j) dw[k][j] = make_float2(0.f, 0.f);
   }
   // fused mode: x is the raw conv output y of the last DoubleConv layer; the activation is
   // recomputed on load and the layer's BatchNorm-backward sums (sum g, sum g*xhat with
@@ -162,107 +170,160 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
   // (the second sum is accumulated as sum g*y and converted to sum g*xhat = invstd*(sum g*y -
   // mean*sum g) once per block, which keeps mean/invstd out of the per-pixel loop)
   constexpr bool fused_bn = FUSED;
-  float sc[8], sh[8], s1[8], s2[8];
+  float2 sc[4], sh[4], s1[4], s2[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = fused_bn ? __ldg(bn_scale + cg * 8 + j) : 1.f;
-    sh[j] = fused_bn ? __ldg(bn_shift + cg * 8 + j) : 0.f;
-    s1[j] = 0.f;
-    s2[j] = 0.f;
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = fused_bn ? make_float2(__ldg(bn_scale + cg * 8 + 2 * j), __ldg(bn_scale + cg * 8 + 2 * j + 1))
+                     : make_float2(1.f, 1.f);
+    sh[j] = fused_bn ? make_float2(__ldg(bn_shift + cg * 8 + 2 * j), __ldg(bn_shift + cg * 8 + 2 * j + 1))
+                     : make_float2(0.f, 0.f);
+    s1[j] = make_float2(0.f, 0.f);
+    s2[j] = make_float2(0.f, 0.f);
   }
   const long total = (long)N * hw;
   const long warps_total = (long)gridDim.x * (kHeadBwdThreads / 32);
-  for (long base = ((long)blockIdx.x * (kHeadBwdThreads / 32) + warp) * kHeadBwdPx; base < total;
-       base += warps_total * kHeadBwdPx) {
-    constexpr int U = kHeadBwdPx / 4;
-    // all loads of the iteration first: U independent 16-byte loads of x per lane, and the
-    // iteration's dlogits as NC coalesced loads (lane L holds pixel base + L) that are then
-    // handed to the 8 lanes of each pixel by shuffles
-    uint4 xin[U];
+  constexpr int U = kHeadBwdPx / 4;
+  // The x vectors of the NEXT iteration are fetched with cp.async into a per-warp shared-memory ring while this
+  // iteration computes: with register loads the warp alternated between a load phase and ~600 issue slots of
+  // arithmetic with nothing in flight (3.6 TB/s at 16 warps per SM).  Every lane reads back exactly the 16 bytes it
+  // copied itself, so the ring needs no barrier -- cp.async.wait_group is per thread.
+  const uint32_t ring = smem_u32(xs) + (uint32_t)(warp * kHeadBwdStages * kHeadBwdPx * 8 + lane) * 16u;   // + (stage*16 + u*4)*128
+  const long x_quad = 4 * ldx, dx_quad = 4 * lddx;       // element stride between a lane's consecutive pixels
+  auto prefetch = [&](long b, int stage) {
+    const __nv_bfloat16* src = x + (b + sub) * ldx + cg * 8;
+    if (b + kHeadBwdPx <= total) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        cp_async_16(ring + (uint32_t)(stage * kHeadBwdPx + u * 4) * 128u, src + u * x_quad, 16u);
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool in = b + u * 4 + sub < total;
+        cp_async_16(ring + (uint32_t)(stage * kHeadBwdPx + u * 4) * 128u, in ? src + u * x_quad : x, in ? 16u : 0u);
+      }
+    }
+    cp_async_commit();
+  };
+  // dlogits of the iteration at `b`: NC coalesced loads, lane L < 16 holds pixel b + L, handed to the 8 lanes of each
+  // pixel by shuffles later.  (img, off) = (b / hw, b % hw) is carried along incrementally: the per-iteration 64-bit
+  // division was a quarter of the kernel's integer instructions.
+  auto load_dl = [&](long b, long img, long off, float (&v)[NC]) {
+    long o = off + lane, n = img;
+    while (o >= hw) { o -= hw; ++n; }
+    const bool in = lane < kHeadBwdPx && b + lane < total;
+    const float* src = dlogits + (n * ncls) * hw + o;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) v[k] = (in && k < ncls) ? __ldg(src + k * hw) : 0.f;
+  };
+  const long step = warps_total * kHeadBwdPx;
+  const long step_img = step / hw, step_off = step - step_img * hw;
+  const long base0 = ((long)blockIdx.x * (kHeadBwdThreads / 32) + warp) * kHeadBwdPx;
+  long img = base0 / hw, off = base0 - img * hw;
+  float dlv[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) dlv[k] = 0.f;
+  if (base0 < total) {
+    prefetch(base0, 0);
+    load_dl(base0, img, off, dlv);
+  }
+  int stage = 0;
+  for (long base = base0; base < total; base += step) {
+    // software pipeline: the NEXT iteration's x vectors (cp.async) and dlogits (registers) are requested before this
+    // iteration's arithmetic; ncu had 21 % of all samples on the first use of the dlogits loaded in the same iteration
+    const long next = base + step;
+    float dl_next[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) dl_next[k] = 0.f;
+    img += step_img;
+    off += step_off;
+    if (off >= hw) { off -= hw; ++img; }
+    if (next < total) {
+      prefetch(next, stage ^ 1);
+      load_dl(next, img, off, dl_next);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    const uint32_t cur = ring + (uint32_t)(stage * kHeadBwdPx) * 128u;
+    stage ^= 1;
+    __nv_bfloat16* dst = dx + (base + sub) * lddx + cg * 8;
+    const bool full = base + kHeadBwdPx <= total;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long px = base + u * 4 + sub;
-      xin[u] = px < total ? ld_nc_v4(x + px * ldx + cg * 8) : make_uint4(0, 0, 0, 0);
-    }
-    float dlv[NC];
-    {
-      const long px = base + lane;
-      const bool in = lane < kHeadBwdPx && px < total;
-      const long n = in ? px / hw : 0, o = in ? px - n * hw : 0;
-#pragma unroll
-      for (int k = 0; k < NC; ++k)
-        dlv[k] = (in && k < ncls) ? __ldg(dlogits + ((long)n * ncls + k) * hw + o) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long px = base + u * 4 + sub;
       float dl[NC];
 #pragma unroll
       for (int k = 0; k < NC; ++k) dl[k] = __shfl_sync(0xffffffffu, dlv[k], u * 4 + sub);
-      float f[8], g[8], yraw[8];
-      unpack8h(xin[u], f);
-      if (fused_bn) {
+      const uint4 xv = ld_shared_v4(cur + (uint32_t)(u * 4) * 128u);   // read where it is used: 12 fewer live registers
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+      float2 f[4], g[4], yraw[4], pre[4];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
+      for (int j = 0; j < 4; ++j) {
+        f[j] = make_float2(bf16_lo(xw[j]), bf16_hi(xw[j]));
+        if (fused_bn) {
           yraw[j] = f[j];
-          yraw[j + 1] = f[j + 1];
-          const uint32_t pk = pack_bf16x2(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f),
-                                          fmaxf(fmaf(f[j + 1], sc[j + 1], sh[j + 1]), 0.f));
-          f[j] = bf16_lo(pk);
-          f[j + 1] = bf16_hi(pk);
+          pre[j] = fma2(f[j], sc[j], sh[j]);       // y * scale + shift: its sign is the ReLU mask
+          const uint32_t pk = pack_bf16x2(fmaxf(pre[j].x, 0.f), fmaxf(pre[j].y, 0.f));
+          f[j] = make_float2(bf16_lo(pk), bf16_hi(pk));
         }
+        g[j] = make_float2(0.f, 0.f);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = 0.f;
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
         const float4 w0 = *reinterpret_cast<const float4*>(sw + k * kHeadC + cg * 8);
         const float4 w1 = *reinterpret_cast<const float4*>(sw + k * kHeadC + cg * 8 + 4);
-        const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float2 wk[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                              make_float2(w1.z, w1.w)};
+        const float2 dl2 = make_float2(dl[k], dl[k]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          g[j] = fmaf(dl[k], wk[j], g[j]);
-          dw[k][j] = fmaf(dl[k], f[j], dw[k][j]);
+        for (int j = 0; j < 4; ++j) {
+          g[j] = fma2(dl2, wk[j], g[j]);
+          dw[k][j] = fma2(dl2, f[j], dw[k][j]);
         }
         db[k] += dl[k];
       }
       uint4 o4;
-      o4.x = pack_bf16x2(g[0], g[1]);
-      o4.y = pack_bf16x2(g[2], g[3]);
-      o4.z = pack_bf16x2(g[4], g[5]);
-      o4.w = pack_bf16x2(g[6], g[7]);
-      if (px < total) *reinterpret_cast<uint4*>(dx + px * lddx + cg * 8) = o4;
+      o4.x = pack_bf16x2(g[0].x, g[0].y);
+      o4.y = pack_bf16x2(g[1].x, g[1].y);
+      o4.z = pack_bf16x2(g[2].x, g[2].y);
+      o4.w = pack_bf16x2(g[3].x, g[3].y);
+      if (full || base + u * 4 + sub < total) *reinterpret_cast<uint4*>(dst + u * dx_quad) = o4;
       if (fused_bn) {
         // the sums use the bf16-rounded dx that is stored (what the apply pass will read);
         // out-of-range pixels have dl = 0, hence contribute exactly 0
-        float gr[8];
-        unpack8h(o4, gr);
+        const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gg = fmaf(yraw[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
-          s1[j] += gg;
-          s2[j] = fmaf(gg, yraw[j], s2[j]);
+        for (int j = 0; j < 4; ++j) {
+          const float2 gg = make_float2(pre[j].x > 0.f ? bf16_lo(ow[j]) : 0.f, pre[j].y > 0.f ? bf16_hi(ow[j]) : 0.f);
+          s1[j] = add2(s1[j], gg);
+          s2[j] = fma2(gg, yraw[j], s2[j]);
         }
       }
     }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) dlv[k] = dl_next[k];
   }
   // reduce the 4 pixel sub-lanes of the warp
+  __syncthreads();   // every warp is done with the ring: `red` aliases it
+  auto quad_sum = [](float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+  };
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dw[k][j] += __shfl_xor_sync(0xffffffffu, dw[k][j], 8);
-      dw[k][j] += __shfl_xor_sync(0xffffffffu, dw[k][j], 16);
-    }
-    db[k] += __shfl_xor_sync(0xffffffffu, db[k], 8);
-    db[k] += __shfl_xor_sync(0xffffffffu, db[k], 16);
+    for (int j = 0; j < 4; ++j) dw[k][j] = make_float2(quad_sum(dw[k][j].x), quad_sum(dw[k][j].y));
+    db[k] = quad_sum(db[k]);
   }
   const int stride = kHeadC + 1;
   if (sub == 0) {
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[(warp * NC + k) * stride + cg * 8 + j] = dw[k][j];
+      for (int j = 0; j < 4; ++j) {
+        red[(warp * NC + k) * stride + cg * 8 + 2 * j] = dw[k][j].x;
+        red[(warp * NC + k) * stride + cg * 8 + 2 * j + 1] = dw[k][j].y;
+      }
       if (cg == 0) red[(warp * NC + k) * stride + kHeadC] = db[k];
     }
   }
@@ -275,18 +336,18 @@ head1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
   }
   if (fused_bn) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
-      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
-      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
-      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+    for (int j = 0; j < 4; ++j) {
+      s1[j] = make_float2(quad_sum(s1[j].x), quad_sum(s1[j].y));
+      s2[j] = make_float2(quad_sum(s2[j].x), quad_sum(s2[j].y));
     }
     __syncthreads();   // `red` is reused: [warp][2][64]
     if (sub == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        red[(warp * 2 + 0) * kHeadC + cg * 8 + j] = s1[j];
-        red[(warp * 2 + 1) * kHeadC + cg * 8 + j] = s2[j];
+      for (int j = 0; j < 4; ++j) {
+        red[(warp * 2 + 0) * kHeadC + cg * 8 + 2 * j] = s1[j].x;
+        red[(warp * 2 + 0) * kHeadC + cg * 8 + 2 * j + 1] = s1[j].y;
+        red[(warp * 2 + 1) * kHeadC + cg * 8 + 2 * j] = s2[j].x;
+        red[(warp * 2 + 1) * kHeadC + cg * 8 + 2 * j + 1] = s2[j].y;
       }
     }
     __syncthreads();

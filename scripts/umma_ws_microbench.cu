@@ -65,16 +65,18 @@ constexpr int kABytes = 80 * 1024;   // a (16+2) x (32+2) halo box of 128-byte r
 constexpr int kBBytes = 256 * 128;
 
 // TILES consecutive 128-row tiles share each B slice.  Issue order as in the conv kernel: per tap, per tile, per K slice.
-template <int N, int MODE, int TILES>
+// COMMIT > 0: a tcgen05.commit to a (never awaited) mbarrier after every COMMIT MMAs, as the conv kernel releases its
+// weight-ring slot after the 8 MMAs of a tap
+template <int N, int MODE, int TILES, int COMMIT = 0>
 __global__ void __launch_bounds__(128, 1) ws_bench(int iters, long long* out_cycles, int* out_count) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + kABytes;
-  const uint32_t bar = base + kABytes + kBBytes, slot = bar + 16;
+  const uint32_t bar = base + kABytes + kBBytes, slot = bar + 16, bar2 = bar + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t o = threadIdx.x * 16; o < kABytes + kBBytes; o += blockDim.x * 16)
     st_shared_v4(base + o, make_uint4(0, 0, 0, 0));
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(slot, 512);
   fence_proxy_async();
   tc_fence_before();
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(128, 1) ws_bench(int iters, long long* out_cyc
               }
             }
             ++count;
+            if (COMMIT > 0 && ((tap * TILES + t) * 4 + k + 1) % COMMIT == 0 && leader) umma_commit(bar2);
           }
         }
       }
@@ -455,6 +458,11 @@ int main() {
     cudaFree(src);
   }
   for (int grid : {1, 148}) {
+    run_kernel(ws_bench<64, PLAIN, 2, 8>, "plain SS + commit every 8 MMAs", 64, 2, it, grid);
+    run_kernel(ws_bench<64, WS_REUSE, 2, 8>, ".ws fill/lastuse + commit every 8", 64, 2, it, grid);
+    run_kernel(ws_bench<64, WS_REUSE, 2, 24>, ".ws fill/lastuse + commit every 24", 64, 2, it, grid);
+    run_kernel(ws_bench<128, PLAIN, 2, 8>, "plain SS + commit every 8 MMAs", 128, 2, it, grid);
+    run_kernel(ws_bench<128, PLAIN, 2, 24>, "plain SS + commit every 24 MMAs", 128, 2, it, grid);
     run_kernel(ws_bench<64, PLAIN, 2>, "plain SS", 64, 2, it, grid);
     run_kernel(ws_bench<64, WS_PLAIN, 2>, ".ws, no collector qualifier", 64, 2, it, grid);
     run_kernel(ws_bench<64, WS_REUSE, 2>, ".ws, b0-b3 fill (tile 0) / lastuse (tile 1)", 64, 2, it, grid);

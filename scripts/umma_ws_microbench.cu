@@ -305,6 +305,129 @@ __global__ void __launch_bounds__(128, 1) ws_bench_fill(int iters, const uint8_t
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+
+// ------------------------------------------------------------------------------------------------ epilogue interference
+// The conv kernel's MMA stream runs beside 8 epilogue warps.  IMODE 1: EW warps issue tcgen05.ld 32x32b.x32 (4 KB each) from
+// TMEM columns the MMAs do not write, DELAY dependent integer operations between two loads (throttle); IMODE 2: EW warps
+// stream 8 st.shared.v4 + 32 ld.shared.u32 per round over a private 4 KB tile (the staging + statistics pattern).
+// Reported: interferer operations per MMA next to the cycles per MMA.  Kernel rates for 64 -> 64 channels: 0.22 tcgen05.ld
+// and 0.11 staging rounds per MMA.
+template <int N, int MODE, int IMODE, int EW, int DELAY>
+__global__ void __launch_bounds__(32 + 32 * EW, 1) ws_bench_epi(int iters, long long* out_cycles, int* out_count,
+                                                                 long long* out_ops) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int TILES = 2;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_base = base, b_base = base + kABytes, e_base = b_base + kBBytes;     // e: EW x 4 KB
+  const uint32_t bar = e_base + 8 * 4096, slot = bar + 8;
+  volatile int* done = reinterpret_cast<volatile int*>(al + kABytes + kBBytes + 8 * 4096 + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t o = threadIdx.x * 16; o < kABytes + kBBytes + 8 * 4096; o += blockDim.x * 16)
+    st_shared_v4(base + o, make_uint4(0, 0, 0, 0));
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); *done = 0; }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(al + kABytes + kBBytes + 8 * 4096 + 8);
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, N, 0, 0);
+  constexpr uint32_t kRB = 128;
+  constexpr int kBoxW = 18;
+  if (warp == 0) {
+    long long t0 = 0, t1 = 0;
+    int count = 0;
+    const bool leader = elect_one();
+    const uint32_t b_lo = smem_desc_lo(b_base, 16);
+    constexpr uint32_t kBHi = smem_desc_hi(8 * kRB, 128);
+    constexpr uint32_t kAHiBox = smem_desc_hi(kBoxW * kRB, 128);
+    const uint32_t a_lo = smem_desc_lo(a_base, 16);
+    __syncwarp();
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int r = tap / 3, s = tap - 3 * r;
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (it | tap) != 0 ? 1u : (k != 0 ? 1u : 0u);
+            const uint32_t d = tmem + t * N;
+            const uint32_t a_off = (uint32_t(r * kBoxW + t * 8 + s) * kRB + k * 32) >> 4;
+            const uint64_t da = smem_desc_join(a_lo + a_off, kAHiBox);
+            const uint64_t db = smem_desc_join(b_lo + ((tap * 4 + k) * 32 >> 4) % 64, kBHi);
+            if (leader) {
+              if (MODE == PLAIN) umma_bf16(d, da, db, kIdesc, acc);
+              else mma_ws_coll(k, t == 0 ? 0 : 2, d, da, db, kIdesc, acc);
+            }
+            ++count;
+          }
+        }
+      }
+    }
+    if (leader) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    t1 = clock64();
+    tc_fence_after();
+    *done = 1;
+    if (lane == 0 && blockIdx.x == 0) { *out_cycles = t1 - t0; *out_count = count; }
+  } else {
+    long long ops = 0;
+    uint32_t sink = 0;
+    const uint32_t tile = e_base + (uint32_t)((warp - 1) & 7) * 4096u;
+    while (!*done) {
+      if (IMODE == 1) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + (uint32_t((warp & 3) * 32) << 16) + 256 + (uint32_t)(ops & 7) * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sink ^= r[j];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(tile + lane * 128 + (uint32_t(q ^ (lane & 7)) << 4), make_uint4(sink, q, lane, 1));
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr)
+          sink += ld_shared_u32(tile + rr * 128 + (uint32_t((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
+        __syncwarp();
+      }
+      ++ops;
+#pragma unroll 1
+      for (int dly = 0; dly < DELAY; ++dly) sink = sink * 1664525u + 1013904223u;
+    }
+    if (sink == 0x12345678u) *out_ops = -1;                       // keep `sink` alive
+    if (blockIdx.x == 0 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(out_ops), (unsigned long long)ops);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <typename K>
+static void run_epi(K kern, const char* name, int N, int ew, int delay, int iters, int grid) {
+  long long *d_cyc, *d_ops; int* d_cnt;
+  cudaMalloc(&d_cyc, 8); cudaMalloc(&d_cnt, 4); cudaMalloc(&d_ops, 8);
+  const int smem = kABytes + kBBytes + 8 * 4096 + 2048;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  kern<<<grid, 32 + 32 * ew, smem>>>(8, d_cyc, d_cnt, d_ops);
+  cudaMemset(d_ops, 0, 8);
+  kern<<<grid, 32 + 32 * ew, smem>>>(iters, d_cyc, d_cnt, d_ops);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0, ops = 0; int cnt = 0;
+  cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&ops, d_ops, 8, cudaMemcpyDeviceToHost);
+  const double per = cnt ? (double)cyc / cnt : 0.0;
+  printf("%-40s N=%3d warps %d delay %4d grid=%3d  %7.1f cycles/MMA   %5.2f interferer ops/MMA   tensor-pipe bound %5.1f %%   %s\n",
+         name, N, ew, delay, grid, per, cnt ? (double)ops / cnt : 0.0, 100.0 * (128.0 * N / 256.0) / per,
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d_cyc); cudaFree(d_cnt); cudaFree(d_ops);
+}
+
 template <typename K>
 static void run_fill(K kern, const char* name, int depth, int iters, int grid, const uint8_t* src) {
   long long *d_cyc, *d_fill; int* d_cnt;
@@ -457,6 +580,21 @@ int main() {
     }
     cudaFree(src);
   }
+  printf("-- MMA stream beside epilogue-like warps: tcgen05.ld (IMODE 1) or staging + statistics shared-memory traffic (IMODE 2)\n");
+  run_epi(ws_bench_epi<64, WS_REUSE, 1, 8, 0>, ".ws N=64 + tcgen05.ld unthrottled", 64, 8, 0, it, 148);
+  run_epi(ws_bench_epi<64, WS_REUSE, 1, 8, 200>, ".ws N=64 + tcgen05.ld", 64, 8, 200, it, 148);
+  run_epi(ws_bench_epi<64, WS_REUSE, 1, 8, 1000>, ".ws N=64 + tcgen05.ld", 64, 8, 1000, it, 148);
+  run_epi(ws_bench_epi<64, WS_REUSE, 1, 8, 4000>, ".ws N=64 + tcgen05.ld", 64, 8, 4000, it, 148);
+  run_epi(ws_bench_epi<64, WS_REUSE, 2, 8, 0>, ".ws N=64 + staging/statistics unthrottled", 64, 8, 0, it, 148);
+  run_epi(ws_bench_epi<64, WS_REUSE, 2, 8, 200>, ".ws N=64 + staging/statistics", 64, 8, 200, it, 148);
+  run_epi(ws_bench_epi<64, WS_REUSE, 2, 8, 1000>, ".ws N=64 + staging/statistics", 64, 8, 1000, it, 148);
+  run_epi(ws_bench_epi<64, WS_REUSE, 2, 8, 4000>, ".ws N=64 + staging/statistics", 64, 8, 4000, it, 148);
+  run_epi(ws_bench_epi<64, PLAIN, 1, 8, 1000>, "plain N=64 + tcgen05.ld", 64, 8, 1000, it, 148);
+  run_epi(ws_bench_epi<64, PLAIN, 2, 8, 1000>, "plain N=64 + staging/statistics", 64, 8, 1000, it, 148);
+  run_epi(ws_bench_epi<128, PLAIN, 1, 4, 0>, "plain N=128 + tcgen05.ld unthrottled", 128, 4, 0, it, 148);
+  run_epi(ws_bench_epi<128, PLAIN, 1, 4, 1000>, "plain N=128 + tcgen05.ld", 128, 4, 1000, it, 148);
+  run_epi(ws_bench_epi<128, PLAIN, 2, 4, 0>, "plain N=128 + staging/statistics unthrottled", 128, 4, 0, it, 148);
+  run_epi(ws_bench_epi<128, PLAIN, 2, 4, 1000>, "plain N=128 + staging/statistics", 128, 4, 1000, it, 148);
   for (int grid : {1, 148}) {
     run_kernel(ws_bench<64, PLAIN, 2, 8>, "plain SS + commit every 8 MMAs", 64, 2, it, grid);
     run_kernel(ws_bench<64, WS_REUSE, 2, 8>, ".ws fill/lastuse + commit every 8", 64, 2, it, grid);

@@ -22,7 +22,8 @@ def strip(l):
     return re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip()
 
 
-MN = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCATOMSWS", "HMMA.16816", "HGMMA", "SYNCS"]
+MN = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCATOMSWS", "HMMA.16816", "HGMMA", "SYNCS", "UTCHMMA.WS", "FFMA2",
+      "LDGSTS"]
 out = ["Round 2 -- SASS evidence, product library floodplanet_code_b200/lib/libfloodplanet_b200.so (sm_100a)",
        "Command: cuobjdump -sass floodplanet_code_b200/lib/libfloodplanet_b200.so   (nvcc 12.9.86, -gencode "
        "arch=compute_100a,code=sm_100a -lineinfo)",
@@ -30,12 +31,14 @@ out = ["Round 2 -- SASS evidence, product library floodplanet_code_b200/lib/libf
        "Whole library mnemonic counts: " + ", ".join(f"{m} x{sum(m in l for l in lines)}" for m in MN),
        "(UTCHMMA = tcgen05.mma kind::f16; LDTM = tcgen05.ld; UTMALDG / UTMASTG = cp.async.bulk.tensor load / store (TMA);",
        " UTCBAR = tcgen05.commit -> mbarrier; UTCATOMSWS = tcgen05.alloc / dealloc; no legacy HMMA.16816 (mma.sync) and no",
-       " HGMMA (wgmma) anywhere in the library)", ""]
+       " HGMMA (wgmma) anywhere in the library; UTCHMMA.WS = tcgen05.mma.ws with collector qualifiers, FFMA2 = fma.rn.f32x2,",
+       " LDGSTS = cp.async -- the last two in the head backward)", ""]
 KERNELS = [
     ("fprop / dgrad: conv3x3_halo_kernel<BN=128, KCH=64, TAPS=9, EW=4>  (the dominant kernel of the step)",
      "conv3x3_halo_kernelILi128ELi64ELi9ELi4E"),
-    ("fprop / dgrad: conv3x3_halo_kernel<BN=64, KCH=64, TAPS=9, EW=8>  (Cout = 64 full-resolution layers)",
-     "conv3x3_halo_kernelILi64ELi64ELi9ELi8E"),
+    ("fprop / dgrad: conv3x3_halo_kernel<BN=64, KCH=64, TAPS=9, EW=8, WS=true>  (Cout = 64 full-resolution layers: "
+     "weight-stationary UTCHMMA.WS, B_KEEP = collector fill by tile 0, B_REUSE = last use by tile 1, BUFFER<k> = K slice)",
+     "conv3x3_halo_kernelILi64ELi64ELi9ELi8ELb1E"),
     ("wgrad: conv3x3_wgrad_kernel<MODE_X_SHIFT=0, NBW=64, NB=2>  (Cout >= 128 layers: three taps stacked on N = 192)",
      "conv3x3_wgrad_kernelILi0ELi64ELi2E"),
     ("wgrad: conv3x3_wgrad_kernel<MODE_RS_SPLIT=4, NBW=64, NB=1>  (Cout = 64 layers: rows stacked on M, taps on N)",

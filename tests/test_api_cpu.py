@@ -45,6 +45,10 @@ def test_kernels_are_blackwell_native_sass():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass  # no legacy mma.sync path
+    # the 64-output-channel halo kernel issues weight-stationary MMAs with collector re-use of the weight slice,
+    # the head backward packed fp32 arithmetic and cp.async staging
+    for mnemonic in ("UTCHMMA.WS", "B_KEEP", "B_REUSE", "FFMA2", "LDGSTS"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_state_dict_layout_equals_reference():

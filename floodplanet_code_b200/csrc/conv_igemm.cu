@@ -477,11 +477,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // FPB200_HALO_WS (experiment switch, read once): bit 0 = weight-stationary MMAs in the 64 -> 64 / 128 -> 64 channel
-// kernel (default on).
+// kernel, bit 1 = in the 128-output-channel kernels with 64-channel chunks; both on by default.  At N = 128 the MMA
+// stream itself is no faster (64 cycles either way) but operand reads drop from 128 to 96 B/clk, which leaves the
+// epilogue's staging / statistics traffic room beside it: +1.5 % fprop, +0.7 % dgrad over the Cout >= 128 layers,
+// +0.6 % on the step (alternating A/B, profiles/r02_ws_halo64_ncu.md).
 static int halo_ws_mask() {
   static const int mask = [] {
     const char* e = getenv("FPB200_HALO_WS");
-    return e != nullptr ? atoi(e) : 1;
+    return e != nullptr ? atoi(e) : 3;
   }();
   return mask;
 }
@@ -564,8 +567,12 @@ static int conv3x3_dispatch(const void* x, long ldx, const void* w_packed, void*
   // one per (quadrant, tile).  Measured (B = 64, 64 -> 128 @ 256^2 fprop with statistics): 0.619 ->
   // 0.476 ms; with two or more K chunks the shallower rings of this variant cost more than the
   // epilogue gains (128 -> 128: 0.834 -> 0.853 ms), and a plain dgrad epilogue has slack either way.
-  if (BN == 128 && KCH == 64 && taps == 9 && Cin == 64 && (p.stats_mode != 0 || scale != nullptr))
+  if (BN == 128 && KCH == 64 && taps == 9 && Cin == 64 && (p.stats_mode != 0 || scale != nullptr)) {
+    if (halo_ws_mask() & 2) return launch_halo<128, 64, 9, 8, true>(tmA, tmB, tmY, tmYL, p, stream);
     return launch_halo<128, 64, 9, 8>(tmA, tmB, tmY, tmYL, p, stream);
+  }
+  if (BN == 128 && KCH == 64 && taps == 9 && (halo_ws_mask() & 2))
+    return launch_halo<128, 64, 9, 4, true>(tmA, tmB, tmY, tmYL, p, stream);
   if (BN == 64 && KCH == 64 && taps == 9 && (halo_ws_mask() & 1))
     return launch_halo<64, 64, 9, 8, true>(tmA, tmB, tmY, tmYL, p, stream);
 #define FP_HALO_CASE(bn, kch, tp) \

@@ -2,7 +2,7 @@
 # in-step A/B of the weight-stationary halo kernel (alternating, same box), then the full GPU suite
 mkdir -p gpurun_out
 for rep in 1 2; do
-  for m in 0 1; do
+  for m in 1 3; do
     FPB200_HALO_WS=$m python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --no-infer > gpurun_out/r3_step_ws${m}_rep${rep}.json 2> gpurun_out/r3_step_ws${m}_rep${rep}.err
     python - <<PY
 import json
@@ -13,5 +13,5 @@ print("ws=${m} rep=${rep}", round(d["value"], 1), "chips/s", round(d["ms_per_ste
 PY
   done
 done
-python -m pytest tests -q -m gpu -x > gpurun_out/r3_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r3_tests.log
-tail -n 3 gpurun_out/r3_tests.log
+
+

@@ -67,6 +67,8 @@ constexpr int kBBytes = 256 * 128;
 // TILES consecutive 128-row tiles share each B slice.  Issue order as in the conv kernel: per tap, per tile, per K slice.
 // COMMIT > 0: a tcgen05.commit to a (never awaited) mbarrier after every COMMIT MMAs, as the conv kernel releases its
 // weight-ring slot after the 8 MMAs of a tap
+__device__ int g_random_fill = 0;   // 1: operands are pseudo-random finite bf16 values instead of zeros (does timing depend on data?)
+
 template <int N, int MODE, int TILES, int COMMIT = 0>
 __global__ void __launch_bounds__(128, 1) ws_bench(int iters, long long* out_cycles, int* out_count) {
   extern __shared__ uint8_t smem_raw[];
@@ -74,9 +76,17 @@ __global__ void __launch_bounds__(128, 1) ws_bench(int iters, long long* out_cyc
   const uint32_t a_base = base, b_base = base + kABytes;
   const uint32_t bar = base + kABytes + kBBytes, slot = bar + 16, bar2 = bar + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (uint32_t o = threadIdx.x * 16; o < kABytes + kBBytes; o += blockDim.x * 16)
-    st_shared_v4(base + o, make_uint4(0, 0, 0, 0));
-  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
+  for (uint32_t o = threadIdx.x * 16; o < kABytes + kBBytes; o += blockDim.x * 16) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g_random_fill) {   // bf16 pairs with exponent 0x3f (|x| in [0.5, 2)), random sign and mantissa
+      uint32_t h = o * 2654435761u + blockIdx.x * 40503u;
+      auto nxt = [&]() { h = h * 1664525u + 1013904223u; return ((h >> 8) & 0x807f807fu) | 0x3f003f00u; };
+      v = make_uint4(nxt(), nxt(), nxt(), nxt());
+    }
+    st_shared_v4(base + o, v);
+  }
+  const uint32_t bar3 = bar + 48;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); mbar_init(bar3, 1); fence_barrier_init(); mbar_arrive(bar3); }
   if (warp == 0) tmem_alloc(slot, 512);
   fence_proxy_async();
   tc_fence_before();
@@ -122,6 +132,13 @@ __global__ void __launch_bounds__(128, 1) ws_bench(int iters, long long* out_cyc
             }
             ++count;
             if (COMMIT > 0 && ((tap * TILES + t) * 4 + k + 1) % COMMIT == 0 && leader) umma_commit(bar2);
+            if (COMMIT < 0 && ((tap * TILES + t) * 4 + k + 1) % (COMMIT < 0 ? -COMMIT : 1) == 0) {
+              // what the conv kernel's issue loop does at a tap boundary: release the weight slot (commit), wait for the
+              // next slot's full barrier (here: a barrier whose phase 0 completed long ago) and fence
+              if (leader) umma_commit(bar2);
+              mbar_wait(bar3, 0);
+              tc_fence_after();
+            }
           }
         }
       }
@@ -595,7 +612,22 @@ int main() {
   run_epi(ws_bench_epi<128, PLAIN, 1, 4, 1000>, "plain N=128 + tcgen05.ld", 128, 4, 1000, it, 148);
   run_epi(ws_bench_epi<128, PLAIN, 2, 4, 0>, "plain N=128 + staging/statistics unthrottled", 128, 4, 0, it, 148);
   run_epi(ws_bench_epi<128, PLAIN, 2, 4, 1000>, "plain N=128 + staging/statistics", 128, 4, 1000, it, 148);
+  {
+    int one = 1, zero = 0;
+    cudaMemcpyToSymbol(g_random_fill, &one, sizeof(int));
+    printf("-- operands = pseudo-random bf16 in +-[0.5, 2) instead of zeros\n");
+    run_kernel(ws_bench<64, PLAIN, 2>, "plain SS, random operands", 64, 2, it, 148);
+    run_kernel(ws_bench<64, WS_REUSE, 2>, ".ws fill / lastuse, random operands", 64, 2, it, 148);
+    run_kernel(ws_bench<128, PLAIN, 2>, "plain SS, random operands", 128, 2, it, 148);
+    run_kernel(ws_bench<128, WS_REUSE, 2>, ".ws fill / lastuse, random operands", 128, 2, it, 148);
+    run_kernel(ws_bench<64, WS_REUSE, 2>, ".ws fill / lastuse, random operands, 20x longer", 64, 2, it * 20, 148);
+    run_kernel(ws_bench<128, PLAIN, 2>, "plain SS, random operands, 20x longer", 128, 2, it * 20, 148);
+    cudaMemcpyToSymbol(g_random_fill, &zero, sizeof(int));
+    printf("-- operands = zeros\n");
+  }
   for (int grid : {1, 148}) {
+    run_kernel(ws_bench<64, WS_REUSE, 2, -8>, ".ws + commit, barrier wait, fence every 8", 64, 2, it, grid);
+    run_kernel(ws_bench<128, PLAIN, 2, -8>, "plain + commit, barrier wait, fence every 8", 128, 2, it, grid);
     run_kernel(ws_bench<64, PLAIN, 2, 8>, "plain SS + commit every 8 MMAs", 64, 2, it, grid);
     run_kernel(ws_bench<64, WS_REUSE, 2, 8>, ".ws fill/lastuse + commit every 8", 64, 2, it, grid);
     run_kernel(ws_bench<64, WS_REUSE, 2, 24>, ".ws fill/lastuse + commit every 24", 64, 2, it, grid);

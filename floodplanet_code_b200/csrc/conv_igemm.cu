@@ -436,8 +436,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (k + 1 < kUnitsPerItem) issue_y(k + 1);
             }
           } else if (do_stats) {
-            // lane l owns channels 2l, 2l+1 of this unit: walk the 32 staged rows
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            // lane l owns channels 2l, 2l+1 of this unit: walk the 32 staged rows.  The channel pair is summed with
+            // packed fp32 instructions (FADD2 / FFMA2: same bits as two scalar operations, half the issue slots -- the
+            // epilogue of the 64-channel layers is instruction bound); tiles that lie entirely inside the image, i.e.
+            // nearly all of them, skip the per-row validity select.
+            float2 sp = make_float2(0.f, 0.f), qp = make_float2(0.f, 0.f);
+            const bool all_valid = vmask == 0xffffffffu;
 #pragma unroll
             for (int r0 = 0; r0 < 32; r0 += 8) {
               uint32_t wv[8];
@@ -446,16 +450,25 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int rr = r0 + j;
                 wv[j] = ld_shared_u32(stg + rr * 128 + (uint32_t((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
               }
+              if (all_valid) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const bool ok = (vmask >> (r0 + j)) & 1u;
-                const float lo = ok ? bf16_lo(wv[j]) : 0.f, hi = ok ? bf16_hi(wv[j]) : 0.f;
-                s0 += lo; s1 += hi;
-                q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+                for (int j = 0; j < 8; ++j) {
+                  const float2 v = make_float2(bf16_lo(wv[j]), bf16_hi(wv[j]));
+                  sp = add2(sp, v);
+                  qp = fma2(v, v, qp);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const bool ok = (vmask >> (r0 + j)) & 1u;
+                  const float2 v = make_float2(ok ? bf16_lo(wv[j]) : 0.f, ok ? bf16_hi(wv[j]) : 0.f);
+                  sp = add2(sp, v);
+                  qp = fma2(v, v, qp);
+                }
               }
             }
-            acc_sum[u][0] += s0; acc_sum[u][1] += s1;
-            acc_sq[u][0] += q0; acc_sq[u][1] += q1;
+            acc_sum[u][0] += sp.x; acc_sum[u][1] += sp.y;
+            acc_sq[u][0] += qp.x; acc_sq[u][1] += qp.y;
           }
         }
       }

@@ -515,15 +515,33 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, long ldda,
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  for (long px = (long)blockIdx.x * TP + pl; px < num_pixels; px += (long)gridDim.x * TP) {
-    float g[8], v[8];
-    unpack8(ld_stream(da + px * ldda + cg * 8), g);
-    unpack8(ld_stream(y + px * ldy + cg * 8), v);
+  // four pixels per iteration, their eight 16-byte loads issued before the first use (one pixel per iteration left
+  // two loads in flight per thread: 5.15 TB/s); the pixels are still accumulated in the same order, so the sums keep
+  // their bits
+  const long stride = (long)gridDim.x * TP;
+  for (long px0 = (long)blockIdx.x * TP + pl; px0 < num_pixels; px0 += 4 * stride) {
+    uint4 gq[4], yq[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-      s1[j] += gg;
-      s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
+    for (int k = 0; k < 4; ++k) {
+      const long px = px0 + k * stride;
+      if (px < num_pixels) {
+        gq[k] = ld_stream(da + px * ldda + cg * 8);
+        yq[k] = ld_stream(y + px * ldy + cg * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (px0 + k * stride < num_pixels) {
+        float g[8], v[8];
+        unpack8(gq[k], g);
+        unpack8(yq[k], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = fmaf(v[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+          s1[j] += gg;
+          s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
+        }
+      }
     }
   }
 #pragma unroll

@@ -43,6 +43,7 @@
 //                  17 % tensor-pipe utilisation, ncu).  Here A = dy unshifted (M = 64), B = x box
 //                  with halo, and the three taps of a filter row are stacked on N (N blocks one
 //                  pixel apart, LBO = one pixel row): 12 MMAs and 42 KB per stage, 0.905 -> 0.652 ms.
+#include <stdlib.h>
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -88,7 +89,7 @@ struct WgCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int MODE, int NBW, int NB>
+template <int MODE, int NBW, int NB, bool ACOLL = false>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                      const WgradParams p) {
@@ -197,10 +198,16 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         const uint32_t a_addr16 = (sa >> 4) & 0x3FFF;
         const uint32_t b_addr16 = (sb >> 4) & 0x3FFF;
         const uint32_t acc = (t > t_begin) ? 1u : 0u;
+        // MODE_X_SHIFT with two input-channel blocks: both groups multiply the SAME dy slice of K step k, so the loops
+        // run K-step-major and the first group parks A in the collector for the second (A is read from shared memory
+        // once per K step: 16 instead of 20 KB of operand reads per pair); ACOLL = false keeps the group-major plain form
+        constexpr bool kShareA = MODE == 0 && NB == 2 && ACOLL;
 #pragma unroll
-        for (int g = 0; g < Cfg::kGroups; ++g) {
+        for (int o = 0; o < (kShareA ? kWgTH : Cfg::kGroups); ++o) {
 #pragma unroll
-          for (int k = 0; k < kWgTH; ++k) {   // K step k = image row k of the tile (16 pixels)
+          for (int i = 0; i < (kShareA ? Cfg::kGroups : kWgTH); ++i) {
+            const int g = kShareA ? i : o;     // accumulator group
+            const int k = kShareA ? o : i;     // K step k = image row k of the tile (16 pixels)
             uint32_t a_lo, b_lo;
             if (MODE == 0) {
               // A: dy rows k*16.. of both 64-co blocks (LBO = block pitch)
@@ -223,9 +230,19 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
               a_lo = (a_addr16 + ((k * kWgTW * 128) >> 4)) | ((uint32_t(Cfg::kABlock) >> 4) << 16);
               b_lo = (b_addr16 + ((((k + g) * kWgBoxW) * kBRow) >> 4)) | ((kBRow >> 4) << 16);
             }
-            if (leader)
-              umma_bf16(tmem_base + g * Cfg::kN, smem_desc_join(a_lo, kAHi),
-                        smem_desc_join(b_lo, kBHi), kIdesc, k == 0 ? acc : 1u);
+            if (leader) {
+              if constexpr (kShareA && ACOLL) {
+                if (g == 0)
+                  umma_bf16_acoll<0>(tmem_base + g * Cfg::kN, smem_desc_join(a_lo, kAHi),
+                                     smem_desc_join(b_lo, kBHi), kIdesc, k == 0 ? acc : 1u);
+                else
+                  umma_bf16_acoll<2>(tmem_base + g * Cfg::kN, smem_desc_join(a_lo, kAHi),
+                                     smem_desc_join(b_lo, kBHi), kIdesc, k == 0 ? acc : 1u);
+              } else {
+                umma_bf16(tmem_base + g * Cfg::kN, smem_desc_join(a_lo, kAHi),
+                          smem_desc_join(b_lo, kBHi), kIdesc, k == 0 ? acc : 1u);
+              }
+            }
           }
         }
         if (leader) umma_commit(empty_bar(stage));
@@ -360,11 +377,11 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, WgPlan* pl, int ta
   return FPB200_OK;
 }
 
-template <int MODE, int NBW, int NB>
+template <int MODE, int NBW, int NB, bool ACOLL = false>
 static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& p,
                         cudaStream_t stream) {
   using Cfg = WgCfg<MODE, NBW, NB>;
-  auto kern = conv3x3_wgrad_kernel<MODE, NBW, NB>;
+  auto kern = conv3x3_wgrad_kernel<MODE, NBW, NB, ACOLL>;
   static bool attr_set[kMaxDevices] = {false};   // cudaFuncSetAttribute is per device
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
@@ -423,7 +440,12 @@ int fpb200_conv3x3_wgrad_bf16_nhwc(const void* x, long ldx, const void* dy, long
   p.ksplit = pl.ksplit; p.n_items = pl.n_items; p.items_ci = pl.items_ci; p.items_r = pl.items_r;
   p.Cout = Cout; p.Cin = Cin; p.taps = 9;
   p.ws = reinterpret_cast<float*>(workspace);
-  if (pl.mode == 0 && pl.nb == 2) rc = launch_wgrad<0, 64, 2>(tmDY, tmX, p, stream);
+  // FPB200_WGRAD_ACOLL (experiment switch, read once; default on): A collector in the two-block MODE_X_SHIFT kernel.
+  // Tensor-bound either way (97 % pipe): +0.5 % over the six layers that use it, 20 % fewer operand reads
+  // (alternating A/B on one box: 6.78 / 6.80 vs 6.76 / 6.74 ms, profiles/r02_wgrad_acoll_ab.txt).
+  static const bool acoll = [] { const char* e = getenv("FPB200_WGRAD_ACOLL"); return e == nullptr || atoi(e) != 0; }();
+  if (pl.mode == 0 && pl.nb == 2 && acoll) rc = launch_wgrad<0, 64, 2, true>(tmDY, tmX, p, stream);
+  else if (pl.mode == 0 && pl.nb == 2) rc = launch_wgrad<0, 64, 2>(tmDY, tmX, p, stream);
   else if (pl.mode == 0) rc = launch_wgrad<0, 64, 1>(tmDY, tmX, p, stream);
   else if (pl.mode == 4) rc = launch_wgrad<4, 64, 1>(tmDY, tmX, p, stream);
   else if (pl.mode == 3 && pl.nbw == 32) rc = launch_wgrad<3, 32, 1>(tmDY, tmX, p, stream);

@@ -184,6 +184,22 @@ __device__ __forceinline__ void umma_bf16_ws(uint32_t tmem_d, uint64_t desc_a, u
   else FP_WS_ASM("b3::lastuse");
 #undef FP_WS_ASM
 }
+// Plain form with the A collector: an MMA issued with collector::a::fill keeps its A operand in the collector and
+// the next MMA(s) issued with ::use / ::lastuse multiply the SAME A with a different B without re-reading A from
+// shared memory (wgrad: one dy slice against the x slices of two input-channel blocks).  OP: 0 fill, 2 lastuse.
+template <int OP>
+__device__ __forceinline__ void umma_bf16_acoll(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc, uint32_t accumulate) {
+  static_assert(OP == 0 || OP == 2, "fill or lastuse");
+  if constexpr (OP == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Arrives (count 1) on the mbarrier once all previously issued MMAs retire.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

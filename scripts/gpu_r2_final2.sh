@@ -2,14 +2,14 @@
 # round 2, last session: final check on one GPU the way the driver runs things (smoke, full GPU suite, reference arm,
 # headline bench), then the ncu launch list of one training step (after the same command exited 0 without ncu)
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2j_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/r2j_smoke.log
-python -m pytest tests -q -m gpu > gpurun_out/r2j_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2j_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2k_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/r2k_smoke.log
+python -m pytest tests -q -m gpu > gpurun_out/r2k_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2k_tests.log
 
-( time python bench.py --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/r2j_bench_n1.json 2> gpurun_out/r2j_bench_n1.err
-for f in gpurun_out/r2j_smoke.log gpurun_out/r2j_tests.log gpurun_out/r2j_bench_n1.err; do echo "== $f"; tail -n 6 $f; done
+( time python bench.py --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/r2k_bench_n1.json 2> gpurun_out/r2k_bench_n1.err
+for f in gpurun_out/r2k_smoke.log gpurun_out/r2k_tests.log gpurun_out/r2k_bench_n1.err; do echo "== $f"; tail -n 6 $f; done
 python - <<'PY'
 import json
-for f in ("gpurun_out/r2j_bench_n1.json",):
+for f in ("gpurun_out/r2k_bench_n1.json",):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, {k: d.get(k) for k in ("value", "ms_per_step", "gpu_launches", "reference_sample")}, d.get("e2e"), d.get("clocks"))
